@@ -1,0 +1,135 @@
+/* libtnrcuda -- C ABI of the B200 (sm_100a) engine behind TNRKit's coarse-graining
+ * hot path.  Plain pointers and sizes only; every tensor is FP64, column major
+ * (first index fastest), i.e. exactly the memory layout of the dense block of a
+ * TensorKit `TensorMap{Float64, ComplexSpace}` whose legs are (codomain..., domain...).
+ * Device pointers are raw CUDA device addresses owned by the caller (the Julia
+ * host's device-resident storage type) unless allocated with tnr_malloc.
+ *
+ * Every entry point cites the reference interface it replaces
+ * (paths relative to VictorVanthilt/TNRKit.jl v0.5.1).
+ *
+ * All functions return 0 on success; nonzero on error (1 = invalid argument,
+ * 2 = CUDA error, 3 = internal).  tnr_last_error(ctx) returns the message.
+ * There is no CPU fallback anywhere: without a CUDA device tnr_create fails.
+ */
+#ifndef TNRCUDA_H
+#define TNRCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tnr_context tnr_context;
+
+/* scheme kinds for tnr_step_out_dims */
+enum {
+    TNR_TRG = 0,
+    TNR_BTRG = 1,
+    TNR_HOTRG = 2,
+    TNR_ATRG = 3,
+    TNR_HOTRG_3D = 4,
+    TNR_ATRG_3D = 5
+};
+
+/* ---- context ----------------------------------------------------------- */
+int tnr_version(void);
+/* `stream` is a cudaStream_t; NULL selects the legacy default stream.  All work of the
+ * context is enqueued on that stream, so it is ordered with the caller's own work there. */
+int tnr_create(int device, void* stream, tnr_context** out);
+int tnr_destroy(tnr_context* ctx);
+const char* tnr_last_error(tnr_context* ctx);
+int tnr_synchronize(tnr_context* ctx);
+/* counters of this library's own kernel launches (bench.py "gpu_launches") */
+int tnr_get_counters(tnr_context* ctx, uint64_t* launches, uint64_t* gemm_launches,
+                     double* gemm_flops, double* permute_bytes);
+int tnr_reset_counters(tnr_context* ctx);
+/* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
+ * library stream; read returns the summed milliseconds, flops and the launch count. */
+int tnr_gemm_timing(tnr_context* ctx, int enable);
+int tnr_gemm_timing_read(tnr_context* ctx, double* ms_total, double* flops_total, int64_t* count);
+
+/* ---- device memory (replaces the host Array storage of TensorMap.data) -- */
+int tnr_malloc(tnr_context* ctx, size_t bytes, void** dptr);
+int tnr_free(tnr_context* ctx, void* dptr);
+int tnr_upload(tnr_context* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int tnr_download(tnr_context* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- primitives --------------------------------------------------------- */
+/* C = alpha op(A) op(B) + beta C  (BLAS dgemm semantics; replaces LinearAlgebra.BLAS.gemm!
+ * as called by TensorOperations.tensorcontract! for every `@tensor` line of the step! bodies,
+ * e.g. src/schemes/trg.jl:42, src/schemes/hotrg3d.jl:116-120).  FP64 tensor cores (DMMA). */
+int tnr_gemm(tnr_context* ctx, char transa, char transb, int m, int n, int k, double alpha,
+             const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+             int64_t ldc);
+int tnr_gemm_strided_batched(tnr_context* ctx, char transa, char transb, int m, int n, int k,
+                             double alpha, const double* A, int64_t lda, int64_t strideA,
+                             const double* B, int64_t ldb, int64_t strideB, double beta,
+                             double* C, int64_t ldc, int64_t strideC, int batch);
+/* dst leg k = src leg perm[k] (0-based); replaces TensorKit.permute / transpose
+ * (src/schemes/hotrg3d.jl:134, atrg.jl:40, atrg3d.jl:37, trg.jl:40). */
+int tnr_permute(tnr_context* ctx, const double* src, double* dst, int rank, const int64_t* dims,
+                const int* perm);
+/* Pairwise contraction by single-character leg labels (einsum for two operands; labels that
+ * appear in A and B but not in C are summed).  Replaces one binary `@tensor` contraction
+ * (TensorOperations.tensorcontract!).  C is written compact in label order labelsC. */
+int tnr_contract(tnr_context* ctx, const double* A, int rankA, const int64_t* dimsA,
+                 const char* labelsA, const double* B, int rankB, const int64_t* dimsB,
+                 const char* labelsB, double* C, const char* labelsC);
+/* svd_trunc(T; trunc = truncrank(chi)) with the first `ncod` legs as codomain
+ * (MatrixAlgebraKit via TensorKit; src/utility/projectors.jl:213-219, btrg.jl:63, atrg.jl:38).
+ * k = min(chi, min(rows, cols)).  U: rows x k, S: k, Vt: k x cols, eps: 2-norm of discarded. */
+int tnr_svd_trunc(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
+                  int chi, double* U, double* S, double* Vt, int64_t* k_out, double* eps_out);
+/* eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) (src/schemes/hotrg.jl:106,114,
+ * hotrg3d.jl:94-98).  Keeps the chi eigenvalues of largest magnitude.  MM is n x n and is
+ * not modified.  W: k signed eigenvalues, V: n x k. */
+int tnr_eigh_trunc(tnr_context* ctx, const double* MM, int64_t n, int chi, double* W, double* V,
+                   int64_t* k_out, double* eps_out);
+
+/* ---- scheme step! / finalize! bodies ------------------------------------ */
+/* Output leg dimensions of one step! for a tensor with legs `dims` (4 for 2D, 6 for 3D). */
+int tnr_step_out_dims(int scheme, const int64_t* dims, int chi, int64_t* dims_out);
+
+/* step!(::TRG, truncrank(chi))      src/schemes/trg.jl:38-44 */
+int tnr_trg_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
+                 int64_t* dims_out);
+/* step!(::BTRG, truncrank(chi))     src/schemes/btrg.jl:62-97.  S1/S2 are the DIAGONALS of the
+ * bond tensors (they are identity / DiagonalTensorMap-valued in the reference), lengths
+ * dims[1] and dims[0]; outputs have lengths dims_out[1], dims_out[0]. */
+int tnr_btrg_step(tnr_context* ctx, const double* T, const int64_t* dims, const double* S1,
+                  const double* S2, double k, int chi, double* Tout, int64_t* dims_out,
+                  double* S1out, double* S2out);
+/* step!(::HOTRG, trunc)             src/schemes/hotrg.jl:155-161 */
+int tnr_hotrg_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
+                   int64_t* dims_out);
+/* step!(::ATRG, trunc)              src/schemes/atrg.jl:37-45 */
+int tnr_atrg_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
+                  int64_t* dims_out);
+/* step!(::HOTRG_3D, trunc)          src/schemes/hotrg3d.jl:131-139 (three _step! + permutes) */
+int tnr_hotrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                     double* Tout, int64_t* dims_out);
+/* _step!(::HOTRG_3D, trunc)         src/schemes/hotrg3d.jl:124-129, restricted to the slices
+ * Tout[:, :, :, :, :, f] with f_begin <= f < f_end of the new open x-bond (multi-GPU sharding:
+ * each rank computes its own slices, the host all-gathers along the last leg).  Tout must be
+ * the full-size buffer; the permute of step! is NOT applied (call tnr_permute). */
+int tnr_hotrg3d_substep(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                        double* Tout, int64_t* dims_out, int64_t f_begin, int64_t f_end);
+/* step!(::ATRG_3D, trunc)           src/schemes/atrg3d.jl:85-97 */
+int tnr_atrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
+                    int64_t* dims_out);
+
+/* finalize!(::Union{TRG,ATRG,HOTRG})  src/utility/finalize.jl:4-8 : n = |T[1 2;2 1]|, T /= n */
+int tnr_finalize_2d(tnr_context* ctx, double* T, const int64_t* dims, double* norm_out);
+/* finalize!(::BTRG)                   src/utility/finalize.jl:10-14 */
+int tnr_finalize_btrg(tnr_context* ctx, double* T, const int64_t* dims, const double* S1,
+                      const double* S2, double* norm_out);
+/* finalize!(::HOTRG_3D / ::ATRG_3D)   src/utility/finalize.jl:56-66 : n = |T[1 1;2 3 2 3]| */
+int tnr_finalize_3d(tnr_context* ctx, double* T, const int64_t* dims, double* norm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNRCUDA_H */

@@ -1,0 +1,128 @@
+"""GPU parity of the primitives (through the C ABI) against numpy on the same inputs."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _up(tk, a):
+    return tk.DeviceTensor.from_numpy(a)
+
+
+def _gemm(tk, ctx, ta, tb, m, n, k, rng, alpha=1.0, beta=0.0):
+    A = rng.standard_normal((k, m) if ta == "T" else (m, k))
+    B = rng.standard_normal((n, k) if tb == "T" else (k, n))
+    C0 = rng.standard_normal((m, n))
+    dA, dB, dC = _up(tk, A), _up(tk, B), _up(tk, C0)
+    ctx.call("tnr_gemm", ta.encode(), tb.encode(), m, n, k, alpha, dA.ptr, A.shape[0], dB.ptr,
+             B.shape[0], beta, dC.ptr, m)
+    ref = alpha * (A.T if ta == "T" else A) @ (B.T if tb == "T" else B) + beta * C0
+    got = dC.to_numpy()
+    return got, ref
+
+
+@pytest.mark.parametrize("ta,tb", list(itertools.product("NT", "NT")))
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (128, 128, 16), (129, 131, 37),
+                                   (300, 24, 577), (64, 200, 4096), (513, 259, 65)])
+def test_gemm_layouts(tk, ctx, ta, tb, m, n, k):
+    rng = np.random.default_rng(m * 1000 + n * 10 + k)
+    got, ref = _gemm(tk, ctx, ta, tb, m, n, k, rng)
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(k)
+
+
+def test_gemm_alpha_beta_splitk(tk, ctx):
+    rng = np.random.default_rng(5)
+    got, ref = _gemm(tk, ctx, "T", "N", 96, 80, 20000, rng, alpha=-0.5, beta=2.0)
+    assert np.abs(got - ref).max() <= 1e-10
+
+
+def test_gemm_strided_batched(tk, ctx):
+    rng = np.random.default_rng(6)
+    nb, m, n, k = 37, 45, 24, 33
+    A = rng.standard_normal((nb, k, m))  # each A_b stored (m x k) column major == (k, m) C order
+    B = rng.standard_normal((n, k))      # (k x n) column major
+    dA = tk.DeviceTensor.from_numpy(np.transpose(A, (2, 1, 0)))
+    dB = tk.DeviceTensor.from_numpy(B.T)
+    dC = tk.DeviceTensor.empty((m, n, nb))
+    ctx.call("tnr_gemm_strided_batched", b"N", b"N", m, n, k, 1.0, dA.ptr, m, m * k, dB.ptr, k, 0,
+             0.0, dC.ptr, m, m * n, nb)
+    got = dC.to_numpy()  # [m, n, nb]
+    for b in range(nb):
+        ref = A[b].T @ B.T
+        assert np.abs(got[:, :, b] - ref).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dims,perm", [
+    ((5,), (0,)), ((4, 7), (1, 0)), ((33, 65), (1, 0)), ((3, 4, 5), (2, 0, 1)),
+    ((2, 3, 4, 5), (1, 3, 0, 2)), ((6, 5, 4, 3, 2, 7), (5, 3, 1, 2, 0, 4)),
+    ((4, 4, 8, 8, 8, 8), (0, 1, 3, 2, 5, 4)), ((8, 8, 8, 8, 8, 8), (1, 3, 5, 0, 2, 4)),
+    ((24, 24, 24), (2, 1, 0)), ((1, 9, 1, 4), (3, 2, 1, 0)), ((40, 3, 40), (0, 2, 1)),
+])
+def test_permute(tk, dims, perm):
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(dims)
+    got = _up(tk, a).permute(perm).to_numpy()
+    assert np.array_equal(got, np.transpose(a, perm))  # bit exact: pure data movement
+
+
+def test_contract(tk):
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((3, 4, 5, 6))
+    b = rng.standard_normal((5, 7, 3))
+    for lc in ("bdf", "fbd", "dfb"):
+        got = tk.contract(_up(tk, a), "abcd", _up(tk, b), "cfa", lc).to_numpy()
+        ref = np.einsum("abcd,cfa->" + lc, a, b)
+        assert np.abs(got - ref).max() <= 1e-12
+    # outer product and full-K-leading / trailing natural layouts
+    x, y = rng.standard_normal((4, 3)), rng.standard_normal((5,))
+    got = tk.contract(_up(tk, x), "ab", _up(tk, y), "c", "abc").to_numpy()
+    assert np.abs(got - np.einsum("ab,c->abc", x, y)).max() <= 1e-14
+
+
+@pytest.mark.parametrize("m,n,chi", [(4, 4, 4), (16, 16, 5), (36, 20, 12), (20, 36, 40),
+                                     (144, 144, 16), (7, 1, 3)])
+def test_svd_trunc(tk, m, n, chi):
+    rng = np.random.default_rng(m + n)
+    a = rng.standard_normal((m, n)) * np.logspace(0, -6, n)[None, :]
+    U, S, Vt, eps = tk.svd_trunc(_up(tk, a), 1, chi)
+    u, s, vt = U.to_numpy(), S.to_numpy(), Vt.to_numpy()
+    sref = np.linalg.svd(a, compute_uv=False)
+    k = min(chi, m, n)
+    assert s.shape == (k,)
+    assert np.abs(s - sref[:k]).max() <= 1e-12 * sref[0]                    # spectrum
+    assert abs(eps - np.linalg.norm(sref[k:])) <= 1e-12 * sref[0]          # truncation error
+    assert np.abs(u.T @ u - np.eye(k)).max() <= 1e-12                      # isometries
+    assert np.abs(vt @ vt.T - np.eye(k)).max() <= 1e-12
+    uu, ss, vv = np.linalg.svd(a, full_matrices=False)
+    best = (uu[:, :k] * ss[:k]) @ vv[:k]
+    assert np.abs((u * s) @ vt - best).max() <= 1e-11 * sref[0]            # gauge invariant
+
+
+def test_svd_rank_deficient(tk):
+    # the initial Ising tensor: 4x4 matrix of rank 2 (exact zero singular values)
+    a = tk.classical_ising().reshape(4, 4)
+    U, S, Vt, eps = tk.svd_trunc(_up(tk, a), 1, 16)
+    u, s, vt = U.to_numpy(), S.to_numpy(), Vt.to_numpy()
+    assert np.all(np.isfinite(u)) and np.all(np.isfinite(vt))
+    assert np.abs((u * s) @ vt - a).max() <= 1e-14
+    assert np.abs(s - np.linalg.svd(a, compute_uv=False)).max() <= 1e-14
+
+
+@pytest.mark.parametrize("n,chi", [(4, 2), (16, 16), (64, 8), (256, 16)])
+def test_eigh_trunc(tk, n, chi):
+    rng = np.random.default_rng(n)
+    g = rng.standard_normal((n, n)) * np.logspace(0, -5, n)[None, :]
+    mm = g @ g.T - 0.01 * np.outer(g[:, 0], g[:, 0])  # mostly PSD, one direction shifted
+    W, V, eps = tk.eigh_trunc(_up(tk, mm), chi)
+    w, v = W.to_numpy(), V.to_numpy()
+    wr = np.linalg.eigvalsh(mm)
+    order = np.argsort(-np.abs(wr))
+    k = min(chi, n)
+    scale = np.abs(wr).max()
+    assert np.abs(w - wr[order[:k]]).max() <= 1e-12 * scale
+    assert abs(eps - np.linalg.norm(wr[order[k:]])) <= 1e-12 * scale
+    assert np.abs(v.T @ v - np.eye(k)).max() <= 1e-12
+    assert np.abs(mm @ v - v * w).max() <= 1e-11 * scale

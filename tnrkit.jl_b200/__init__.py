@@ -1,0 +1,20 @@
+"""tnrkit.jl_b200 -- B200-native engine for TNRKit's coarse-graining hot path.
+
+Host-side mirror (Python; Julia is not available in this image) of the reference
+interface for that path: scheme constructors, `run!`, `truncrank`, `maxiter`,
+`classical_*` models, `free_energy`.  Everything numerical runs in `lib/libtnrcuda.so`
+(hand-written CUDA for sm_100a) through the C ABI declared in include/tnrcuda.h."""
+from . import _lib
+from ._lib import Context, TNRCudaError, default_context
+from .free_energy import free_energy
+from .models import (Trivial, Z2Irrep, ZNIrrep, classical_ising, classical_ising_3D,
+                     classical_potts, f_onsager, ising_bc, ising_bc_3D, ising_βc, ising_βc_3D,
+                     potts_bc, potts_βc)
+from .schemes import (ATRG, ATRG_3D, BTRG, HOTRG, HOTRG_3D, TRG, Finalizer, TNRScheme,
+                      allgather_last_leg, beta_sweep, default_Finalizer, finalize, run, run_,
+                      shard_range)
+from .stopping import MultipleCrit, convcrit, maxiter, stopcrit, trivial_convcrit
+from .tensor import DeviceTensor, contract, eigh_trunc, svd_trunc
+from .truncation import truncrank, trunctol
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,124 @@
+// Common definitions for libtnrcuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace tnr {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define TNR_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            throw ::tnr::Error(2, std::string(#expr) + ": " + cudaGetErrorString(_e) +   \
+                                      " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define TNR_CHECK(cond, msg)                                                             \
+    do {                                                                                 \
+        if (!(cond))                                                                     \
+            throw ::tnr::Error(1, std::string(msg) + " [" #cond "] at " + __FILE__ +     \
+                                      ":" + std::to_string(__LINE__));                   \
+    } while (0)
+
+// Counters the bench reads back: how many of OUR kernels were launched.
+struct Counters {
+    unsigned long long launches = 0;       // all kernels of this library
+    unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
+    double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
+    double permute_bytes = 0.0;            // read+write bytes moved by permute kernels
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = 148;
+    Counters ctr;
+    // optional timing of the big GEMM (dominant kernel) with events on ctx->stream
+    bool time_gemm = false;
+    double timed_flops = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    std::string last_error;
+    // multi-GPU sharding of the HOTRG_3D open bond (set by tnr_set_shard)
+    int rank = 0, world = 1;
+};
+
+// ---- device memory (stream ordered) ----
+double* dalloc(Context* ctx, size_t n_doubles);
+void dfree(Context* ctx, void* p);
+
+// ---- kernels: gemm_dmma.cu ----
+// C(m x n, ldc) = alpha * op(A) * op(B) + beta * C, column major, FP64 tensor cores.
+// Batched with two batch levels: batch index b = b1 + nb1*b2 (b1 < nb1, b2 < nb2),
+// operand offset = b1*s1 + b2*s2 (in doubles).
+struct GemmBatch {
+    int nb1 = 1, nb2 = 1;
+    long long sA1 = 0, sA2 = 0, sB1 = 0, sB2 = 0, sC1 = 0, sC2 = 0;
+};
+void gemm(Context* ctx, char transa, char transb, int m, int n, int k, double alpha,
+          const double* A, long long lda, const double* B, long long ldb, double beta,
+          double* C, long long ldc, const GemmBatch& batch = GemmBatch());
+
+// ---- kernels: permute.cu ----
+// dst[sum i_j*dstride_j] = src[sum i_j*sstride_j] for all multi-indices i < dims.
+void strided_copy(Context* ctx, const double* src, double* dst, int rank,
+                  const long long* dims, const long long* sstride, const long long* dstride);
+// dst (compact, column major, dims[perm[k]]) leg k = src leg perm[k]
+void permute(Context* ctx, const double* src, double* dst, int rank, const long long* dims,
+             const int* perm);
+
+// ---- kernels: elementwise.cu ----
+void scale(Context* ctx, double* x, long long n, double alpha);
+// x[i] *= 1 / *dev_scalar
+void scale_inv_dev(Context* ctx, double* x, long long n, const double* dev_scalar);
+// A(m x n, lda): A[:,j] *= f(s[j]) (cols) or A[i,:] *= f(s[i]) (rows)
+// mode: 0 identity, 1 sqrt, 2 pseudopow(s, p)
+void diag_scale(Context* ctx, double* A, long long m, long long n, long long lda,
+                const double* s, bool rows, int mode, double p);
+void vec_map(Context* ctx, const double* s, double* out, long long n, int mode, double p);
+// generic strided trace-like reduction: out = | sum_i x[off + i*stride pattern] |
+// sum over multi-index i<dims of src[sum i_j*stride_j]; result written to dev out (abs if absval)
+void strided_sum(Context* ctx, const double* src, int rank, const long long* dims,
+                 const long long* stride, double* dev_out, bool absval);
+void strided_sum_w(Context* ctx, const double* src, int rank, const long long* dims,
+                   const long long* stride, const double* const* weights, double* dev_out,
+                   bool absval);
+// A viewed as [m1][n][m2] (column major): A[i,j,k] *= f(s[j])
+void axis_scale(Context* ctx, double* A, long long m1, long long n, long long m2, const double* s,
+                int mode, double p);
+void symmetrize(Context* ctx, double* A, long long n);  // A = (A + A^T)/2
+void set_identity(Context* ctx, double* A, long long n);
+void fill_zero(Context* ctx, double* A, long long n);
+// dot of two strided "vectors" with weights: out = |sum_{i,j..}|, used by BTRG finalize
+// dst = flag ? a : b, flag = (*epsA > *epsB)  (device side choice, HOTRG projector pick)
+void select_copy(Context* ctx, double* dst, const double* a, const double* b, long long n,
+                 const double* eps_a, const double* eps_b, double* eps_out);
+
+// ---- kernels: jacobi.cu ----
+// One-sided Jacobi on the columns of G (m x n, ldg), accumulating V (n x n, ldv) when V != null.
+// On return G = A*V has mutually orthogonal columns.  Returns number of sweeps.
+int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long long ldg,
+                         double* V, long long ldv);
+// after orthogonalization: vals[j] = ||g_j|| (svd) or v_j . g_j (eigh, signed)
+void column_values(Context* ctx, const double* G, long long m, long long n, long long ldg,
+                   const double* V, long long ldv, double* vals, bool signed_rayleigh);
+// rank[j] = position of |vals[j]| in descending order (stable); eps = sqrt(sum_{rank>=k} vals^2)
+void rank_select(Context* ctx, const double* vals, long long n, long long k, int* rank,
+                 double* dev_eps);
+// dst[:, rank[j]] = src[:, j] * (normalize ? 1/|vals[j]| : 1) for rank[j] < k ; dst ld = ldd
+void gather_columns(Context* ctx, const double* src, long long m, long long n, long long lds,
+                    const int* rank, long long k, double* dst, long long ldd,
+                    const double* vals, bool normalize);
+void gather_values(Context* ctx, const double* vals, long long n, const int* rank, long long k,
+                   double* out, bool absval);
+
+}  // namespace tnr

@@ -1,0 +1,198 @@
+// Index permutation / strided copy kernels (HBM-bound).
+//
+// Replaces TensorKit `permute` / `transpose` (StridedViews copies) used between
+// the contractions of every step! body (e.g. /root/reference/src/schemes/hotrg3d.jl:134,
+// atrg.jl:40, atrg3d.jl:37).
+//
+// A permutation is a strided copy dst[i.dstride] = src[i.sstride].  After merging
+// index groups that stay adjacent, either the fastest index is the same on both
+// sides (vectorisable row copy) or it differs, in which case a 32x32 tile over
+// (src-fastest, dst-fastest) is transposed through padded shared memory so both
+// the global reads and the global writes are coalesced.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tnr {
+namespace {
+
+constexpr int MAXR = 8;
+
+struct CopyParams {
+    int rank;                // number of "outer" dims (excluding tile dims for the tiled kernel)
+    long long dims[MAXR];
+    long long ss[MAXR];
+    long long ds[MAXR];
+    // tile dims (tiled kernel) / inner dim (row kernel)
+    long long ni, si_s, si_d;  // src-fastest dim: extent, src stride, dst stride
+    long long nj, sj_s, sj_d;  // dst-fastest dim
+    long long tiles_i, tiles_j;
+    long long total;           // total elements (row kernel)
+};
+
+__global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restrict__ src,
+                                                         double* __restrict__ dst,
+                                                         const CopyParams p) {
+    __shared__ double tile[32][33];
+    long long bid = blockIdx.x;
+    long long ti = bid % p.tiles_i;
+    bid /= p.tiles_i;
+    long long tj = bid % p.tiles_j;
+    bid /= p.tiles_j;
+    long long soff = 0, doff = 0;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+        if (d < p.rank) {
+            long long i = bid % p.dims[d];
+            bid /= p.dims[d];
+            soff += i * p.ss[d];
+            doff += i * p.ds[d];
+        }
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    long long i0 = ti * 32, j0 = tj * 32;
+    // read: tx along i (src contiguous), rows along j
+    long long i = i0 + tx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        long long j = j0 + ty + 8 * r;
+        if (i < p.ni && j < p.nj) tile[ty + 8 * r][tx] = src[soff + i * p.si_s + j * p.sj_s];
+    }
+    __syncthreads();
+    // write: tx along j (dst contiguous), rows along i
+    long long j = j0 + tx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        long long ii = i0 + ty + 8 * r;
+        if (ii < p.ni && j < p.nj) dst[doff + ii * p.si_d + j * p.sj_d] = tile[tx][ty + 8 * r];
+    }
+}
+
+// same fastest index on both sides: one thread per element, inner index fastest
+__global__ void __launch_bounds__(256) copy_rows_kernel(const double* __restrict__ src,
+                                                        double* __restrict__ dst,
+                                                        const CopyParams p) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= p.total) return;
+    long long i = idx % p.ni;
+    long long rest = idx / p.ni;
+    long long soff = i * p.si_s, doff = i * p.si_d;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+        if (d < p.rank) {
+            long long k = rest % p.dims[d];
+            rest /= p.dims[d];
+            soff += k * p.ss[d];
+            doff += k * p.ds[d];
+        }
+    }
+    dst[doff] = src[soff];
+}
+
+// contiguous copy, 16-byte vectorised
+__global__ void __launch_bounds__(256) copy_flat_kernel(const double* __restrict__ src,
+                                                        double* __restrict__ dst, long long n,
+                                                        int vec) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (vec) {
+        long long n2 = n / 2;
+        if (idx < n2)
+            reinterpret_cast<double2*>(dst)[idx] = reinterpret_cast<const double2*>(src)[idx];
+        if (idx == 0 && (n & 1)) dst[n - 1] = src[n - 1];
+    } else if (idx < n) {
+        dst[idx] = src[idx];
+    }
+}
+
+}  // namespace
+
+void strided_copy(Context* ctx, const double* src, double* dst, int rank, const long long* dims,
+                  const long long* sstride, const long long* dstride) {
+    TNR_CHECK(rank >= 0 && rank <= 16, "strided_copy: rank out of range");
+    struct D { long long n, s, d; };
+    std::vector<D> v;
+    long long total = 1;
+    for (int i = 0; i < rank; ++i) {
+        TNR_CHECK(dims[i] >= 0, "strided_copy: negative dim");
+        total *= dims[i];
+        if (dims[i] != 1) v.push_back({dims[i], sstride[i], dstride[i]});
+    }
+    if (total == 0) return;
+    // order by destination stride, then merge groups that are adjacent on both sides
+    std::stable_sort(v.begin(), v.end(), [](const D& a, const D& b) { return a.d < b.d; });
+    std::vector<D> m;
+    for (auto& x : v) {
+        if (!m.empty() && m.back().s * m.back().n == x.s && m.back().d * m.back().n == x.d)
+            m.back().n *= x.n;
+        else
+            m.push_back(x);
+    }
+    ctx->ctr.permute_bytes += 16.0 * (double)total;
+    if (m.empty()) {  // single element
+        m.push_back({1, 1, 1});
+    }
+    if (m.size() == 1 && m[0].s == 1 && m[0].d == 1) {
+        int vec = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+        long long work = vec ? (total + 1) / 2 : total;
+        copy_flat_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(src, dst, total, vec);
+        TNR_CUDA(cudaGetLastError());
+        ctx->ctr.launches++;
+        return;
+    }
+    TNR_CHECK((int)m.size() <= MAXR + 2, "strided_copy: too many index groups after merging");
+    // dst-fastest is m[0]; find src-fastest
+    size_t js = 0;
+    for (size_t i = 1; i < m.size(); ++i)
+        if (m[i].s < m[js].s) js = i;
+    CopyParams p{};
+    if (js == 0) {
+        p.ni = m[0].n; p.si_s = m[0].s; p.si_d = m[0].d;
+        p.rank = 0;
+        for (size_t i = 1; i < m.size(); ++i) {
+            p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
+            p.rank++;
+        }
+        p.total = total;
+        copy_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, p);
+    } else {
+        p.ni = m[js].n; p.si_s = m[js].s; p.si_d = m[js].d;
+        p.nj = m[0].n; p.sj_s = m[0].s; p.sj_d = m[0].d;
+        p.rank = 0;
+        long long outer = 1;
+        for (size_t i = 1; i < m.size(); ++i) {
+            if (i == js) continue;
+            p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
+            p.rank++;
+            outer *= m[i].n;
+        }
+        p.tiles_i = (p.ni + 31) / 32;
+        p.tiles_j = (p.nj + 31) / 32;
+        long long blocks = p.tiles_i * p.tiles_j * outer;
+        TNR_CHECK(blocks < (1LL << 31), "strided_copy: grid too large");
+        copy_tiled_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, dst, p);
+    }
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
+void permute(Context* ctx, const double* src, double* dst, int rank, const long long* dims,
+             const int* perm) {
+    TNR_CHECK(rank >= 1 && rank <= 16, "permute: rank out of range");
+    long long sst[16], dims_out[16], dst_st[16], src_st_for_out[16];
+    long long s = 1;
+    std::vector<bool> seen(rank, false);
+    for (int i = 0; i < rank; ++i) { sst[i] = s; s *= dims[i]; }
+    long long d = 1;
+    for (int k = 0; k < rank; ++k) {
+        int q = perm[k];
+        TNR_CHECK(q >= 0 && q < rank && !seen[q], "permute: invalid permutation");
+        seen[q] = true;
+        dims_out[k] = dims[q];
+        dst_st[k] = d;
+        d *= dims[q];
+        src_st_for_out[k] = sst[q];
+    }
+    strided_copy(ctx, src, dst, rank, dims_out, src_st_for_out, dst_st);
+}
+
+}  // namespace tnr

@@ -1,0 +1,21 @@
+// Scheme-level entry points (dense sector).  See schemes.cu.
+#pragma once
+#include "tensor.hpp"
+
+namespace tnr {
+
+double finalize_2d(Context* ctx, DT& T);
+double finalize_btrg(Context* ctx, DT& T, const DT& S1, const DT& S2);
+double finalize_3d(Context* ctx, DT& T);
+
+DT trg_step(Context* ctx, const DT& T, int chi);
+void btrg_step(Context* ctx, DT& T, DT& S1, DT& S2, double kexp, int chi);
+DT hotrg_step(Context* ctx, const DT& T, int chi);
+DT atrg_step(Context* ctx, const DT& T, int chi);
+
+Dims hotrg3d_substep_dims(const Dims& d, int chi);
+void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0, long long f1);
+DT hotrg3d_step(Context* ctx, const DT& T, int chi);
+DT atrg3d_step(Context* ctx, const DT& T, int chi);
+
+}  // namespace tnr

@@ -1,0 +1,83 @@
+// Host-side device tensor + pairwise contraction / truncated factorizations.
+// Column major (first index fastest), matching Julia / TensorKit dense blocks.
+#pragma once
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tnr {
+
+using Dims = std::vector<long long>;
+
+inline long long prod(const Dims& d, size_t a = 0, size_t b = (size_t)-1) {
+    long long p = 1;
+    const size_t e = b < d.size() ? b : d.size();
+    for (size_t i = a; i < e; ++i) p *= d[i];
+    return p;
+}
+
+// Device tensor: owns stream-ordered memory unless constructed as a view.
+struct DT {
+    Context* ctx = nullptr;
+    double* p = nullptr;
+    Dims d;
+    bool owns = false;
+
+    DT() = default;
+    DT(Context* c, const Dims& dims) : ctx(c), d(dims), owns(true) {
+        p = dalloc(c, (size_t)std::max<long long>(prod(dims), 1));
+    }
+    static DT view(Context* c, double* ptr, const Dims& dims) {
+        DT t;
+        t.ctx = c; t.p = ptr; t.d = dims; t.owns = false;
+        return t;
+    }
+    DT(const DT&) = delete;
+    DT& operator=(const DT&) = delete;
+    DT(DT&& o) noexcept { *this = std::move(o); }
+    DT& operator=(DT&& o) noexcept {
+        if (this != &o) {
+            release();
+            ctx = o.ctx; p = o.p; d = std::move(o.d); owns = o.owns;
+            o.p = nullptr; o.owns = false;
+        }
+        return *this;
+    }
+    ~DT() { release(); }
+    void release() {
+        if (owns && p) dfree(ctx, p);
+        p = nullptr; owns = false;
+    }
+    long long size() const { return prod(d); }
+    int rank() const { return (int)d.size(); }
+    DT reshaped(const Dims& nd) && {  // same storage, new shape
+        DT t = std::move(*this);
+        t.d = nd;
+        return t;
+    }
+};
+
+DT clone(const DT& a);
+DT permute(const DT& a, const std::vector<int>& perm);
+// out labels = lc; contracted labels = those in both la and lb and not in lc
+DT contract(const DT& A, const std::string& la, const DT& B, const std::string& lb,
+            const std::string& lc);
+
+struct Trunc {
+    DT U;    // [cod..., k]
+    DT S;    // [k]   singular values (svd) / signed eigenvalues (eigh)
+    DT Vt;   // [k, dom...]  (svd only)
+    DT eps;  // [1] device scalar: 2-norm of the discarded values
+};
+// svd_trunc(T; trunc = truncrank(chi)) with the first ncod legs as codomain
+Trunc svd_trunc(const DT& T, int ncod, int chi);
+// eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)); MM is [cod..., cod...]
+Trunc eigh_trunc(DT MM, int ncod, int chi);
+// R-equivalent of left_orth (QR): returns R' (min(m,n) x n) with R'^T R' = A^T A, where A is T
+// with the first ncod legs as rows.  R' = S V^T differs from the Householder R by a left
+// orthogonal factor, which cancels in every use the reference makes of it (atrg3d.jl:53-66).
+DT orth_r(const DT& T, int ncod);
+
+}  // namespace tnr

@@ -1,0 +1,243 @@
+// Pairwise contraction (TTGT: transpose-transpose-GEMM-transpose with the transposes
+// skipped whenever the operand is already a matrix in one of the layouts the DMMA
+// kernel reads natively) and the truncated factorizations built on the Jacobi engine.
+#include <algorithm>
+
+#include "tensor.hpp"
+
+namespace tnr {
+
+double* dalloc(Context* ctx, size_t n) {
+    void* p = nullptr;
+    TNR_CUDA(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(double), ctx->stream));
+    return (double*)p;
+}
+void dfree(Context* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+DT clone(const DT& a) {
+    DT r(a.ctx, a.d);
+    TNR_CUDA(cudaMemcpyAsync(r.p, a.p, a.size() * sizeof(double), cudaMemcpyDeviceToDevice,
+                             a.ctx->stream));
+    return r;
+}
+
+DT permute(const DT& a, const std::vector<int>& perm) {
+    TNR_CHECK((int)perm.size() == a.rank(), "permute: rank mismatch");
+    Dims nd(perm.size());
+    for (size_t k = 0; k < perm.size(); ++k) nd[k] = a.d[perm[k]];
+    DT r(a.ctx, nd);
+    permute(a.ctx, a.p, r.p, a.rank(), a.d.data(), perm.data());
+    return r;
+}
+
+namespace {
+
+// Is `sub` (ordered) exactly the leading / trailing block of `all`?
+bool is_prefix(const std::string& all, const std::string& sub) {
+    return all.size() >= sub.size() && all.compare(0, sub.size(), sub) == 0;
+}
+bool is_suffix(const std::string& all, const std::string& sub) {
+    return all.size() >= sub.size() &&
+           all.compare(all.size() - sub.size(), sub.size(), sub) == 0;
+}
+std::string filter(const std::string& s, const std::string& keep, bool in) {
+    std::string r;
+    for (char c : s)
+        if ((keep.find(c) != std::string::npos) == in) r.push_back(c);
+    return r;
+}
+std::vector<int> perm_to(const std::string& from, const std::string& to) {
+    std::vector<int> p(to.size());
+    for (size_t k = 0; k < to.size(); ++k) {
+        size_t q = from.find(to[k]);
+        TNR_CHECK(q != std::string::npos, "contract: label not found");
+        p[k] = (int)q;
+    }
+    return p;
+}
+long long dim_of(const DT& t, const std::string& labels, const std::string& sub) {
+    long long p = 1;
+    for (char c : sub) p *= t.d[labels.find(c)];
+    return p;
+}
+
+}  // namespace
+
+DT contract(const DT& A, const std::string& la, const DT& B, const std::string& lb,
+            const std::string& lc) {
+    Context* ctx = A.ctx;
+    TNR_CHECK((int)la.size() == A.rank() && (int)lb.size() == B.rank(), "contract: label count");
+    std::string kA = filter(filter(la, lb, true), lc, false);  // contracted, A order
+    std::string kB = filter(filter(lb, la, true), lc, false);  // contracted, B order
+    std::string fa = filter(la, kA, false), fb = filter(lb, kB, false);
+    TNR_CHECK(kA.size() == kB.size(), "contract: inconsistent labels");
+    TNR_CHECK(fa.size() + fb.size() == lc.size(), "contract: batch/outer labels unsupported");
+    for (char c : kA)
+        TNR_CHECK(A.d[la.find(c)] == B.d[lb.find(c)], "contract: contracted dims differ");
+
+    // choose the K order: prefer an operand that is already in matrix form
+    bool a_nat = is_prefix(la, kA) || is_suffix(la, kA);
+    bool b_nat = is_prefix(lb, kB) || is_suffix(lb, kB);
+    std::string K = a_nat ? kA : (b_nat ? kB : kA);
+    if (K.empty()) K = "";
+
+    // operand A -> (M x K) 'N' [fa K] or (K x M) 'T' [K fa]
+    DT Atmp, Btmp;
+    const double* pa = A.p;
+    const double* pb = B.p;
+    char ta, tb;
+    long long M = dim_of(A, la, fa), N = dim_of(B, lb, fb), Kd = dim_of(A, la, K);
+    if (la == fa + K) ta = 'N';
+    else if (la == K + fa) ta = 'T';
+    else {
+        Atmp = permute(A, perm_to(la, K + fa));
+        pa = Atmp.p;
+        ta = 'T';
+    }
+    if (lb == K + fb) tb = 'N';
+    else if (lb == fb + K) tb = 'T';
+    else {
+        Btmp = permute(B, perm_to(lb, K + fb));
+        pb = Btmp.p;
+        tb = 'N';
+    }
+    Dims cd;
+    std::string nat = fa + fb;
+    for (char c : fa) cd.push_back(A.d[la.find(c)]);
+    for (char c : fb) cd.push_back(B.d[lb.find(c)]);
+    TNR_CHECK(M < (1LL << 31) && N < (1LL << 31) && Kd < (1LL << 31), "contract: dim overflow");
+
+    if (K.empty()) Kd = 1;  // outer product: (M x 1) * (1 x N)
+    long long lda = (ta == 'N') ? M : Kd, ldb = (tb == 'N') ? Kd : N;
+
+    if (nat == lc) {
+        DT C(ctx, cd);
+        gemm(ctx, ta, tb, (int)M, (int)N, (int)Kd, 1.0, pa, lda, pb, ldb, 0.0, C.p, M);
+        return C;
+    }
+    if (fb + fa == lc) {  // C^T = op(B)^T op(A)^T : swap operands, flip transposes
+        Dims cd2;
+        for (char c : fb) cd2.push_back(B.d[lb.find(c)]);
+        for (char c : fa) cd2.push_back(A.d[la.find(c)]);
+        DT C(ctx, cd2);
+        gemm(ctx, tb == 'N' ? 'T' : 'N', ta == 'N' ? 'T' : 'N', (int)N, (int)M, (int)Kd, 1.0, pb,
+             ldb, pa, lda, 0.0, C.p, N);
+        return C;
+    }
+    DT Cn(ctx, cd);
+    gemm(ctx, ta, tb, (int)M, (int)N, (int)Kd, 1.0, pa, lda, pb, ldb, 0.0, Cn.p, M);
+    Atmp.release();
+    Btmp.release();
+    return permute(Cn, perm_to(nat, lc));
+}
+
+// ---------------------------------------------------------------------------
+// truncated factorizations
+// ---------------------------------------------------------------------------
+namespace {
+
+struct IntBuf {
+    Context* ctx;
+    int* p = nullptr;
+    IntBuf(Context* c, size_t n) : ctx(c) {
+        TNR_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(n, 1) * sizeof(int), c->stream));
+    }
+    ~IntBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
+};
+
+DT transpose2d(const DT& a, long long m, long long n) {  // a is m x n -> n x m
+    DT v = DT::view(a.ctx, a.p, {m, n});
+    return permute(v, {1, 0});
+}
+
+}  // namespace
+
+Trunc svd_trunc(const DT& T, int ncod, int chi) {
+    Context* ctx = T.ctx;
+    long long m = prod(T.d, 0, ncod), n = prod(T.d, ncod);
+    long long r = std::min(m, n), k = std::min<long long>(chi, r);
+    Dims cod(T.d.begin(), T.d.begin() + ncod), dom(T.d.begin() + ncod, T.d.end());
+    Trunc out;
+    Dims ud = cod; ud.push_back(k);
+    Dims vd = {k}; vd.insert(vd.end(), dom.begin(), dom.end());
+    out.U = DT(ctx, ud);
+    out.S = DT(ctx, {k});
+    out.Vt = DT(ctx, vd);
+    out.eps = DT(ctx, {1});
+    bool tall = (m >= n);
+    long long gm = tall ? m : n, gn = tall ? n : m;  // G is gm x gn with gm >= gn
+    DT G = tall ? clone(T) : transpose2d(T, m, n);
+    DT V(ctx, {gn, gn});
+    set_identity(ctx, V.p, gn);
+    jacobi_orthogonalize(ctx, G.p, gm, gn, gm, V.p, gn);
+    DT vals(ctx, {gn});
+    column_values(ctx, G.p, gm, gn, gm, nullptr, 0, vals.p, false);
+    IntBuf rank(ctx, gn);
+    rank_select(ctx, vals.p, gn, k, rank.p, out.eps.p);
+    gather_values(ctx, vals.p, gn, rank.p, k, out.S.p, true);
+    if (tall) {
+        // A = (G/|g|) S V^T
+        gather_columns(ctx, G.p, gm, gn, gm, rank.p, k, out.U.p, m, vals.p, true);
+        DT Vk(ctx, {gn, k});
+        gather_columns(ctx, V.p, gn, gn, gn, rank.p, k, Vk.p, gn, nullptr, false);
+        long long dd[2] = {gn, k};
+        int pp[2] = {1, 0};
+        permute(ctx, Vk.p, out.Vt.p, 2, dd, pp);
+    } else {
+        // A^T = (G/|g|) S V^T  ->  A = V S (G/|g|)^T
+        gather_columns(ctx, V.p, gn, gn, gn, rank.p, k, out.U.p, m, nullptr, false);
+        DT Gk(ctx, {gm, k});
+        gather_columns(ctx, G.p, gm, gn, gm, rank.p, k, Gk.p, gm, vals.p, true);
+        long long dd[2] = {gm, k};
+        int pp[2] = {1, 0};
+        permute(ctx, Gk.p, out.Vt.p, 2, dd, pp);
+    }
+    return out;
+}
+
+Trunc eigh_trunc(DT MM, int ncod, int chi) {
+    Context* ctx = MM.ctx;
+    long long n = prod(MM.d, 0, ncod);
+    TNR_CHECK(prod(MM.d, ncod) == n, "eigh_trunc: matrix must be square");
+    long long k = std::min<long long>(chi, n);
+    Dims cod(MM.d.begin(), MM.d.begin() + ncod);
+    Trunc out;
+    Dims ud = cod; ud.push_back(k);
+    out.U = DT(ctx, ud);
+    out.S = DT(ctx, {k});
+    out.eps = DT(ctx, {1});
+    symmetrize(ctx, MM.p, n);  // project_hermitian!
+    DT V(ctx, {n, n});
+    set_identity(ctx, V.p, n);
+    jacobi_orthogonalize(ctx, MM.p, n, n, n, V.p, n);  // MM <- MM*V = V*Lambda
+    DT vals(ctx, {n});
+    column_values(ctx, MM.p, n, n, n, V.p, n, vals.p, true);
+    IntBuf rank(ctx, n);
+    rank_select(ctx, vals.p, n, k, rank.p, out.eps.p);
+    gather_values(ctx, vals.p, n, rank.p, k, out.S.p, false);
+    gather_columns(ctx, V.p, n, n, n, rank.p, k, out.U.p, n, nullptr, false);
+    return out;
+}
+
+DT orth_r(const DT& T, int ncod) {
+    Context* ctx = T.ctx;
+    long long m = prod(T.d, 0, ncod), n = prod(T.d, ncod);
+    TNR_CHECK(m >= n, "orth_r: expects a tall matrix");
+    DT G = clone(T);
+    DT V(ctx, {n, n});
+    set_identity(ctx, V.p, n);
+    jacobi_orthogonalize(ctx, G.p, m, n, m, V.p, n);
+    DT vals(ctx, {n});
+    column_values(ctx, G.p, m, n, m, nullptr, 0, vals.p, false);
+    // R' = S V^T  (n x n):  R'[i, j] = s_i V[j, i]
+    DT R(ctx, {n, n});
+    long long dd[2] = {n, n};
+    int pp[2] = {1, 0};
+    permute(ctx, V.p, R.p, 2, dd, pp);
+    diag_scale(ctx, R.p, n, n, n, vals.p, true, 0, 0.0);
+    return R;
+}
+
+}  // namespace tnr

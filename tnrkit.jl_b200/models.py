@@ -1,0 +1,138 @@
+"""Model constructors -- host side, unchanged in spirit from /root/reference/src/models
+(`src/models stays unchanged; model tensors are built on the host and uploaded once`).
+
+Each constructor returns a host `numpy` array indexed [leg1, leg2, ...] in the reference's
+leg convention (2D: V1 (x) V2 <- V3 (x) V4, 3D: D U' <- N E S' W').  `Z2Irrep` / `ZNIrrep`
+variants return the tensor in the charge basis (every leg graded by the irrep label); the
+engine currently stores them densely, which reproduces the symmetric result whenever the
+truncation does not cut through an exactly degenerate multiplet."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class Trivial:
+    """No symmetry (TensorKit.Trivial)."""
+
+
+class Z2Irrep:
+    """Z2 symmetry labels (TensorKitSectors.Z2Irrep)."""
+
+
+class ZNIrrep:
+    """ZN symmetry labels; use ZNIrrep[N] (TensorKitSectors.ZNIrrep{N})."""
+
+    _cache = {}
+
+    def __class_getitem__(cls, n):
+        if n not in cls._cache:
+            cls._cache[n] = type(f"Z{n}Irrep", (cls,), {"N": int(n)})
+        return cls._cache[n]
+
+
+# src/models/ising.jl:1-8
+ising_βc = math.log(1.0 + math.sqrt(2.0)) / 2.0
+ising_bc = ising_βc
+f_onsager = -2.10965114460820745966777928351108478082549327543540531781696107967700291143188
+ising_βc_3D = 1.0 / 4.51152469
+ising_bc_3D = ising_βc_3D
+
+
+def potts_βc(q):
+    """src/models/potts.jl:40"""
+    return math.log(1.0 + math.sqrt(q))
+
+
+potts_bc = potts_βc
+
+
+def _split(args, default_sym):
+    sym = default_sym
+    rest = list(args)
+    if rest and isinstance(rest[0], type):
+        sym = rest.pop(0)
+    return sym, rest
+
+
+def classical_ising(*args, h=0.0):
+    """classical_ising([symmetry], [beta]; h)  -- src/models/ising.jl:35-66.
+    Default symmetry Z2Irrep, default beta = ising_βc."""
+    sym, rest = _split(args, Z2Irrep)
+    beta = float(rest[0]) if rest else ising_βc
+    if sym is Trivial:
+        init = np.zeros((2, 2, 2, 2))
+        for idx in np.ndindex(2, 2, 2, 2):
+            init[idx] = math.cosh(h * beta) if sum(idx) % 2 == 0 else math.sinh(h * beta)
+        b = np.diag([math.sqrt(math.cosh(beta)), math.sqrt(math.sinh(beta))])
+        return 2.0 * np.einsum("abcd,ia,jb,ck,dl->ijkl", init, b, b, b, b)
+    if sym is Z2Irrep:
+        if h != 0.0:
+            raise AssertionError("External magnetic field is not compatible with Z2 symmetry")
+        x, y = math.cosh(beta), math.sinh(beta)
+        t = np.zeros((2, 2, 2, 2))
+        # coupled sector 0: uncoupled (0,0),(1,1); sector 1: (1,0),(0,1)
+        b0 = [[2 * x * x, 2 * x * y], [2 * x * y, 2 * y * y]]
+        b1 = [[2 * x * y, 2 * x * y], [2 * x * y, 2 * x * y]]
+        for blk, pairs in ((b0, [(0, 0), (1, 1)]), (b1, [(1, 0), (0, 1)])):
+            for r, (i, j) in enumerate(pairs):
+                for c, (k, l) in enumerate(pairs):
+                    t[i, j, k, l] = blk[r][c]
+        return t
+    raise TypeError(f"classical_ising: unsupported symmetry {sym}")
+
+
+def classical_ising_3D(*args, J=1.0):
+    """classical_ising_3D([symmetry], [beta]; J)  -- src/models/ising.jl:125-165."""
+    sym, rest = _split(args, Z2Irrep)
+    beta = float(rest[0]) if rest else ising_βc_3D
+    K = beta * J
+    if sym is Trivial:
+        t = np.array([[math.exp(K), math.exp(-K)], [math.exp(-K), math.exp(K)]])
+        w, v = np.linalg.eigh(t)
+        q = v @ np.diag(np.sqrt(w)) @ v
+        O = np.zeros((2,) * 6)
+        O[(0,) * 6] = 1.0
+        O[(1,) * 6] = 1.0
+        return np.einsum("abcdef,ia,jb,kc,ld,me,nf->ijklmn", O, q, q, q, q, q, q)
+    if sym is Z2Irrep:
+        x, y = math.cosh(K), math.sinh(K)
+        W = np.array([[math.sqrt(x), math.sqrt(y)], [math.sqrt(x), -math.sqrt(y)]])
+        t = np.einsum("ai,aj,ak,al,am,an->ijklmn", W, W, W, W, W, W)
+        return np.ascontiguousarray(np.transpose(t, (0, 3, 4, 5, 1, 2)))
+    raise TypeError(f"classical_ising_3D: unsupported symmetry {sym}")
+
+
+def potts_tensor(q, beta):
+    """src/models/potts.jl:21-30"""
+    A = np.zeros((q,) * 4)
+    for i, j, k, l in np.ndindex(q, q, q, q):
+        E = -(int(i == j) + int(j == l) + int(k == l) + int(k == i))
+        A[i, j, k, l] = math.exp(-beta * E)
+    return A
+
+
+def classical_potts(*args):
+    """classical_potts([symmetry], q, [beta])  -- src/models/potts.jl:63-82."""
+    sym, rest = _split(args, None)
+    q = int(rest[0])
+    beta = float(rest[1]) if len(rest) > 1 else potts_βc(q)
+    if sym is None:
+        sym = ZNIrrep[q]
+    A = potts_tensor(q, beta)
+    if sym is Trivial:
+        return A
+    if isinstance(sym, type) and issubclass(sym, ZNIrrep):
+        if sym.N != q:
+            raise AssertionError("number of irreps must match the number of states")
+        w = np.exp(2j * math.pi / q)
+        Wm = np.array([[w ** (r * c) for c in range(q)] for r in range(q)]) / math.sqrt(q)
+        # ((P' (x) P') * A * (P (x) P)).data reshaped (q,q,q,q), column major as in Julia
+        Pk = np.kron(Wm, Wm)  # row index (i,j) with j fastest <-> column-major pair (j,i)
+        Am = A.reshape(q * q, q * q, order="F")
+        Pcm = np.kron(Wm, Wm)
+        U = Pcm.conj().T @ Am @ Pcm
+        Ud = U.reshape((q, q, q, q), order="F")
+        return np.ascontiguousarray(Ud.real)
+    raise TypeError(f"classical_potts: unsupported symmetry {sym}")

@@ -1,0 +1,284 @@
+"""TNR schemes behind the unchanged `run!(scheme, truncrank(chi), maxiter(n))` API.
+
+Mirrors /root/reference/src/schemes/{tnrscheme,trg,btrg,hotrg,atrg,hotrg3d,atrg3d}.jl and
+src/utility/finalize.jl: same constructor names, same fields (`T`, `S1`, `S2`, `k`), same
+`step!` / `finalize!` split, same `run!` loop and return value (the list of norms).  All
+arithmetic happens in libtnrcuda through the C ABI; this file only sequences calls."""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import time
+
+import numpy as np
+
+from . import _lib
+from .stopping import maxiter, stopcrit
+from .tensor import DeviceTensor
+from .truncation import TruncationStrategy, truncrank
+
+log = logging.getLogger("tnrkit.jl_b200")
+
+
+def _chi(trunc) -> int:
+    if not isinstance(trunc, truncrank):
+        raise NotImplementedError(
+            f"{trunc!r}: only truncrank(chi) is implemented on the B200 path")
+    return trunc.chi
+
+
+class Finalizer:
+    """Finalizer(f!, E): function applied after every step (tnrscheme.jl:16-26)."""
+
+    def __init__(self, f, E=float):
+        self.f = f
+        self.E = E
+
+
+class TNRScheme:
+    kind = None
+    nlegs = 4
+
+    def __init__(self, T, ctx=None):
+        if isinstance(T, DeviceTensor):
+            self.T = T
+        else:
+            T = np.asarray(T, dtype=np.float64)
+            if T.ndim != self.nlegs:
+                raise TypeError(f"{type(self).__name__} expects a tensor with {self.nlegs} legs")
+            self.T = DeviceTensor.from_numpy(T, 2, ctx)
+        self.ctx = self.T.ctx
+
+    # -- step!/finalize! ------------------------------------------------------
+    def _out_dims(self, chi):
+        n = self.nlegs
+        out = (C.c_int64 * n)()
+        rc = self.ctx.lib.tnr_step_out_dims(self.kind, _lib.i64(self.T.dims), chi, out)
+        self.ctx.check(rc, "tnr_step_out_dims")
+        return tuple(out)
+
+    _step_fn = None
+
+    def step(self, trunc):
+        chi = _chi(trunc)
+        od = self._out_dims(chi)
+        out = DeviceTensor.empty(od, 2, self.ctx)
+        dims_out = (C.c_int64 * self.nlegs)()
+        self.ctx.call(self._step_fn, self.T.ptr, _lib.i64(self.T.dims), chi, out.ptr, dims_out)
+        assert tuple(dims_out) == od, (tuple(dims_out), od)
+        self.T = out
+        return self
+
+    def finalize(self):
+        n = C.c_double()
+        fn = "tnr_finalize_2d" if self.nlegs == 4 else "tnr_finalize_3d"
+        self.ctx.call(fn, self.T.ptr, _lib.i64(self.T.dims), C.byref(n))
+        return n.value
+
+    def __repr__(self):
+        return f"{type(self).__name__}(T: {self.T.dims})"
+
+
+class TRG(TNRScheme):
+    """Tensor Renormalization Group (trg.jl)."""
+    kind = _lib.TNR_TRG
+    _step_fn = "tnr_trg_step"
+
+
+class HOTRG(TNRScheme):
+    """Higher-Order TRG (hotrg.jl)."""
+    kind = _lib.TNR_HOTRG
+    _step_fn = "tnr_hotrg_step"
+
+
+class ATRG(TNRScheme):
+    """Anisotropic TRG (atrg.jl)."""
+    kind = _lib.TNR_ATRG
+    _step_fn = "tnr_atrg_step"
+
+
+class ATRG_3D(TNRScheme):
+    """3D Anisotropic TRG (atrg3d.jl)."""
+    kind = _lib.TNR_ATRG_3D
+    nlegs = 6
+    _step_fn = "tnr_atrg3d_step"
+
+
+class BTRG(TNRScheme):
+    """Bond-weighted TRG (btrg.jl): fields T, S1 (vertical bonds), S2 (horizontal), k."""
+    kind = _lib.TNR_BTRG
+
+    def __init__(self, T, k=-0.5, ctx=None):
+        super().__init__(T, ctx)
+        # S1 = id(space(T,2)), S2 = id(space(T,1)); stored as diagonals
+        self.S1 = DeviceTensor.from_numpy(np.ones(self.T.dims[1]), 1, self.ctx)
+        self.S2 = DeviceTensor.from_numpy(np.ones(self.T.dims[0]), 1, self.ctx)
+        self.k = float(k)
+
+    def step(self, trunc):
+        chi = _chi(trunc)
+        od = self._out_dims(chi)
+        out = DeviceTensor.empty(od, 2, self.ctx)
+        s1 = DeviceTensor.empty((od[1],), 1, self.ctx)
+        s2 = DeviceTensor.empty((od[0],), 1, self.ctx)
+        dims_out = (C.c_int64 * 4)()
+        self.ctx.call("tnr_btrg_step", self.T.ptr, _lib.i64(self.T.dims), self.S1.ptr,
+                      self.S2.ptr, self.k, chi, out.ptr, dims_out, s1.ptr, s2.ptr)
+        assert tuple(dims_out) == od, (tuple(dims_out), od)
+        self.T, self.S1, self.S2 = out, s1, s2
+        return self
+
+    def finalize(self):
+        n = C.c_double()
+        self.ctx.call("tnr_finalize_btrg", self.T.ptr, _lib.i64(self.T.dims), self.S1.ptr,
+                      self.S2.ptr, C.byref(n))
+        return n.value
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block of the open bond owned by `rank` (equal blocks when world | n)."""
+    per = -(-n // world)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def allgather_last_leg(buf, dims, group=None):
+    """All-gather of a column-major tensor sharded along its LAST leg (contiguous slabs).
+    Every rank holds the full-size buffer with only its own slab valid."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = int(dims[-1])
+    slab = math.prod(int(d) for d in dims[:-1])
+    if n % world == 0:
+        per = n // world
+        mine = buf[rank * per * slab:(rank + 1) * per * slab]
+        dist.all_gather_into_tensor(buf[: n * slab], mine, group=group)
+    else:
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            if hi > lo:
+                dist.broadcast(buf[lo * slab: hi * slab], src=dist.get_global_rank(group, r)
+                               if group is not None else r, group=group)
+    return buf
+
+
+class HOTRG_3D(TNRScheme):
+    """3D Higher-Order TRG (hotrg3d.jl).
+
+    With `torch.distributed` initialised (one process per GPU) and `shard=True`, every
+    z-compression shards the chi^11 contraction along the new open x-bond: rank r computes
+    T'[..., f] for its block of f and the blocks are all-gathered over NCCL (no other
+    data-path collective)."""
+    kind = _lib.TNR_HOTRG_3D
+    nlegs = 6
+    _step_fn = "tnr_hotrg3d_step"
+    PERM = (5, 3, 1, 2, 0, 4)  # ((6,4),(2,3,1,5))
+
+    def __init__(self, T, ctx=None, shard=None, group=None):
+        super().__init__(T, ctx)
+        self.group = group
+        if shard is None:
+            try:
+                import torch.distributed as dist
+
+                shard = dist.is_available() and dist.is_initialized() and \
+                    dist.get_world_size(group) > 1
+            except Exception:
+                shard = False
+        self.shard = bool(shard)
+
+    def _substep(self, chi):
+        import torch.distributed as dist
+
+        d = self.T.dims
+        od = (d[0], d[1], min(chi, d[4] * d[4]), min(chi, d[5] * d[5]),
+              min(chi, d[4] * d[4]), min(chi, d[5] * d[5]))
+        out = DeviceTensor.empty(od, 2, self.ctx)
+        if self.shard:
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        else:
+            world, rank = 1, 0
+        lo, hi = shard_range(od[5], rank, world)
+        dims_out = (C.c_int64 * 6)()
+        self.ctx.call("tnr_hotrg3d_substep", self.T.ptr, _lib.i64(d), chi, out.ptr, dims_out,
+                      lo, hi)
+        if world > 1:
+            allgather_last_leg(out.buf, od, self.group)
+        self.T = out.permute(self.PERM)
+
+    def step(self, trunc):
+        chi = _chi(trunc)
+        for _ in range(3):
+            self._substep(chi)
+        return self
+
+
+def finalize(scheme):
+    """finalize!(scheme): normalise the tensor by its trace norm and return the norm."""
+    return scheme.finalize()
+
+
+default_Finalizer = Finalizer(finalize, float)
+
+
+def run(scheme, trscheme, criterion=None, finalizer=None, finalize_beginning=True, verbosity=1):
+    """run!(scheme, trscheme, criterion[, finalizer]; finalize_beginning=true, verbosity=1)
+    -- tnrscheme.jl:31-59.  Returns the list of finalizer outputs (norms)."""
+    if not isinstance(trscheme, TruncationStrategy):
+        raise TypeError("run!: second argument must be a truncation strategy")
+    criterion = criterion if criterion is not None else maxiter(100)
+    if not isinstance(criterion, stopcrit):
+        raise TypeError("run!: third argument must be a stopping criterion")
+    finalizer = finalizer or default_Finalizer
+    data = []
+    if verbosity >= 1:
+        log.info("Starting simulation\n %r\n", scheme)
+    if finalize_beginning:
+        data.append(finalizer.f(scheme))
+    steps = 0
+    crit = True
+    t0 = time.perf_counter()
+    while crit:
+        if verbosity >= 2:
+            log.info("Step %d, data[end]: %s", steps + 1, data[-1] if data else "empty")
+        scheme.step(trscheme)
+        data.append(finalizer.f(scheme))
+        steps += 1
+        crit = criterion(steps, data)
+    if verbosity >= 1:
+        log.info("Simulation finished\n %s\n Elapsed time: %.3fs\n Iterations: %d",
+                 criterion.info(steps, data), time.perf_counter() - t0, steps)
+    return data
+
+
+run_ = run  # `run!`
+
+
+def beta_sweep(scheme_cls, model, betas, trscheme, criterion, **scheme_kwargs):
+    """beta-sweep: one independent scheme per GPU, no collectives on the data path.
+    Rank r handles betas[r::world]; results are gathered as Python objects at the end."""
+    try:
+        import torch.distributed as dist
+
+        on = dist.is_available() and dist.is_initialized()
+    except Exception:
+        on = False
+    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    mine = {}
+    for i in range(rank, len(betas), world):
+        kw = dict(scheme_kwargs)
+        if scheme_cls is HOTRG_3D:
+            kw["shard"] = False
+        scheme = scheme_cls(model(betas[i]), **kw)
+        mine[i] = run(scheme, trscheme, criterion, verbosity=0)
+    if not on or world == 1:
+        return [mine[i] for i in range(len(betas))]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    merged = {}
+    for g in gathered:
+        merged.update(g)
+    return [merged[i] for i in range(len(betas))]
