@@ -468,3 +468,11 @@ def free_energy(data, beta, scalefactor=2.0, initial_size=1.0):
     for i, z in enumerate(data, start=1):
         lnz += math.log(z) * scalefactor ** (x - i)
     return -lnz / beta
+
+
+def hotrg3d_chunk_contract(Qk, Pk):
+    """The dominant contraction of HOTRG_3D._contract for one (f, d) pair of open bonds:
+    R[(a y1' y1), (y2 b y2')] = sum_(z x1' x2) Qk[(z x1' x2), (a y1' y1)] Pk[(z x1' x2), ...]
+    (hotrg3d.jl:116-120 after absorbing Ux into A1 and A2).  Used by bench.py's cpu_baseline
+    leg as the bounded CPU sample of the workload."""
+    return Qk.T @ Pk

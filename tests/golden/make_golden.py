@@ -1,0 +1,28 @@
+"""Generates tests/golden/oracle_norms.json from the CPU oracle (oracle/tnr_oracle.py).
+
+The oracle itself is pinned to the reference's published numbers (README.md:81 and the
+rtol's of test/schemes.jl) by tests/test_oracle_golden.py; the reference is Julia and there
+is no Julia toolchain in this image, so vectors cannot be generated from the reference
+directly.  Run:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import tnr_oracle as o  # noqa: E402
+
+out = {}
+T2 = o.classical_ising_z2basis()
+out["BTRG_ising_z2_chi16_it25"] = o.run(o.BTRG(T2), 16, 25)
+out["TRG_ising_z2_chi16_it12"] = o.run(o.TRG(T2), 16, 12)
+out["HOTRG_ising_z2_chi12_it8"] = o.run(o.HOTRG(T2), 12, 8)
+out["ATRG_ising_z2_chi12_it8"] = o.run(o.ATRG(T2), 12, 8)
+T3 = o.classical_ising_3D()
+out["HOTRG_3D_ising_trivial_chi6_it4"] = o.run(o.HOTRG_3D(T3), 6, 4)
+out["HOTRG_3D_ising_trivial_chi8_it3"] = o.run(o.HOTRG_3D(T3), 8, 3)
+out["ATRG_3D_ising_z2_chi6_it4"] = o.run(o.ATRG_3D(o.classical_ising_3D_z2basis()), 6, 4)
+with open(os.path.join(HERE, "oracle_norms.json"), "w") as f:
+    json.dump(out, f, indent=1)
+print({k: len(v) for k, v in out.items()})

@@ -85,3 +85,20 @@ def test_atrg3d_norms_match_oracle(tk):
     T = tk.classical_ising_3D()
     got, ref = _norms(tk, tk.ATRG_3D, o.ATRG_3D, T, 4, 3)
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+
+
+def test_golden_fixture_norms(tk):
+    """Committed oracle vectors (tests/golden/oracle_norms.json, made by make_golden.py)."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_norms.json")))
+    cases = [("TRG_ising_z2_chi16_it12", tk.TRG, tk.classical_ising(), 16, 12),
+             ("HOTRG_ising_z2_chi12_it8", tk.HOTRG, tk.classical_ising(), 12, 8),
+             ("ATRG_ising_z2_chi12_it8", tk.ATRG, tk.classical_ising(), 12, 8),
+             ("HOTRG_3D_ising_trivial_chi6_it4", tk.HOTRG_3D, tk.classical_ising_3D(tk.Trivial), 6, 4),
+             ("ATRG_3D_ising_z2_chi6_it4", tk.ATRG_3D, tk.classical_ising_3D(), 6, 4)]
+    for key, cls, T, chi, n in cases:
+        got = np.array(tk.run(cls(T), tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+        ref = np.array(g[key])
+        assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL, key

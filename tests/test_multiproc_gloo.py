@@ -1,0 +1,61 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: open-bond slab ownership and the
+all-gather along the last leg used by the sharded HOTRG_3D step."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, dims, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tnrkit.jl_b200 as tk
+
+    n = dims[-1]
+    slab = int(np.prod(dims[:-1]))
+    full = torch.arange(slab * n, dtype=torch.float64) * 0.5 + 1.0  # the "true" tensor
+    buf = torch.full((slab * n,), float("nan"), dtype=torch.float64)
+    lo, hi = tk.shard_range(n, rank, world)
+    buf[lo * slab: hi * slab] = full[lo * slab: hi * slab]  # what tnr_hotrg3d_substep fills
+    tk.allgather_last_leg(buf, dims)
+    ok = bool(torch.equal(buf, full))
+    # beta sweep bookkeeping: rank r owns betas[r::world]
+    mine = list(range(rank, 5, world))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    q.put((rank, ok, sorted(sum(gathered, []))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims", [(2, 3, 4), (3, 2, 5)])  # even split and ragged split
+def test_allgather_last_leg_world2(dims):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dims, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, betas in res:
+        assert ok, f"rank {rank}: gathered tensor differs"
+        assert betas == [0, 1, 2, 3, 4]

@@ -1,0 +1,65 @@
+"""Pins the CPU oracle to every golden number the reference holds for the hot path.
+
+README.md:76-81        BTRG, truncrank(16), maxiter(25) at ising_βc: f = -2.1096504926141826902647832
+test/schemes.jl:26     TRG   chi=24 it=25  rtol 2e-6 vs f_onsager
+test/schemes.jl:65     BTRG  chi=24 it=25  rtol 6e-8
+test/schemes.jl:103    HOTRG chi=16 it=25  rtol 6e-7 (scalefactor 4)
+test/schemes.jl:141    ATRG  chi=24 it=25  rtol 3e-6 (scalefactor 4)
+test/schemes.jl:360    ATRG_3D  chi=12 it=25 rtol 5e-3 vs -3.507 (scalefactor 8)
+test/schemes.jl:370    HOTRG_3D chi=8  it=25 rtol 1e-3 vs -3.507
+(all of them on the Z2-symmetric model; the dense charge-basis tensor reproduces it.)
+"""
+import numpy as np
+import pytest
+
+import tnr_oracle as o
+
+
+def rel(a, b):
+    return abs((a - b) / b)
+
+
+def test_readme_quickstart_golden():
+    d = o.run(o.BTRG(o.classical_ising_z2basis()), 16, 25)
+    assert len(d) == 26
+    f = o.free_energy(d, o.ising_bc)
+    assert rel(f, -2.1096504926141826902647832) < 1e-13
+    assert abs(rel(f, o.f_onsager) - 3.1e-7) < 0.05e-7
+    # the Trivial (no symmetry) tensor is the same network in another gauge
+    f2 = o.free_energy(o.run(o.BTRG(o.classical_ising()), 16, 25), o.ising_bc)
+    assert rel(f2, f) < 1e-12
+
+
+@pytest.mark.parametrize("cls,chi,sf,tol", [(o.TRG, 24, 2.0, 2e-6), (o.BTRG, 24, 2.0, 6e-8),
+                                            (o.HOTRG, 16, 4.0, 6e-7), (o.ATRG, 24, 4.0, 3e-6)])
+def test_2d_schemes_reference_tolerances(cls, chi, sf, tol):
+    d = o.run(cls(o.classical_ising_z2basis()), chi, 25)
+    assert rel(o.free_energy(d, o.ising_bc, scalefactor=sf), o.f_onsager) < tol
+
+
+def test_hotrg3d_reference_tolerance():
+    d = o.run(o.HOTRG_3D(o.classical_ising_3D_z2basis()), 8, 25)
+    assert rel(o.free_energy(d, o.ising_bc_3D, scalefactor=8.0), o.f_benchmark3D) < 1e-3
+
+
+def test_atrg3d_reference_tolerance():
+    # the reference runs 25 iterations (218 s here); the series sum_i log(z_i) 8^(1-i) has
+    # converged to 1e-5 relative after 5, which is far inside the 5e-3 tolerance.
+    d = o.run(o.ATRG_3D(o.classical_ising_3D_z2basis()), 12, 5)
+    assert rel(o.free_energy(d, o.ising_bc_3D, scalefactor=8.0), o.f_benchmark3D) < 5e-3
+
+
+def test_models_potts_3state():
+    # test/models.jl:16: TRG chi=16 it=25 on classical_potts(Trivial, 3): -4.119552029995684, rtol 1e-3
+    d = o.run(o.TRG(o.classical_potts(3)), 16, 25)
+    assert rel(o.free_energy(d, o.potts_bc(3)), -4.119552029995684) < 1e-3
+
+
+def test_free_energy_and_driver_semantics():
+    # run! pushes one norm before the first step (finalize_beginning) and one per step
+    s = o.TRG(o.classical_ising())
+    assert len(o.run(s, 4, 3)) == 4
+    assert len(o.run(o.TRG(o.classical_ising()), 4, 3, finalize_beginning=False)) == 3
+    # free_energy: lnz = sum_i log(z_i) * sf^(x - i), x = 1 - log(initial)/log(sf)
+    assert np.isclose(o.free_energy([np.e, np.e], 2.0), -(1.0 + 0.5) / 2.0)
+    assert np.isclose(o.free_energy([np.e], 1.0, scalefactor=4.0, initial_size=4.0), -0.25)
