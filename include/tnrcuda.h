@@ -46,6 +46,10 @@ int tnr_synchronize(tnr_context* ctx);
 int tnr_get_counters(tnr_context* ctx, uint64_t* launches, uint64_t* gemm_launches,
                      double* gemm_flops, double* permute_bytes);
 int tnr_reset_counters(tnr_context* ctx);
+/* counters of the warp-specialised TMA GEMM (subset of gemm_launches) */
+int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
+/* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests) */
+int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
  * library stream; read returns the summed milliseconds, flops and the launch count. */
 int tnr_gemm_timing(tnr_context* ctx, int enable);

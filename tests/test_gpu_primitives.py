@@ -126,3 +126,23 @@ def test_eigh_trunc(tk, n, chi):
     assert abs(eps - np.linalg.norm(wr[order[k:]])) <= 1e-12 * scale
     assert np.abs(v.T @ v - np.eye(k)).max() <= 1e-12
     assert np.abs(mm @ v - v * w).max() <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("m,n,k,alpha,beta", [(1664, 1664, 96, 1.0, 0.0), (1601, 1555, 77, -0.5, 2.0),
+                                              (2048, 1536, 1000, 1.0, 0.0), (1538, 1666, 64, 2.0, 1.0)])
+def test_gemm_tma_path(tk, ctx, m, n, k, alpha, beta):
+    """TN problems with >= 148 tiles take the TMA/mbarrier kernel (ragged edges are zero
+    filled by the tensor map); the result must equal numpy and the cp.async kernel."""
+    rng = np.random.default_rng(m + n + k)
+    before = ctx.counters()["tma_gemm_launches"]
+    got, ref = _gemm(tk, ctx, "T", "N", m, n, k, rng, alpha, beta)
+    assert ctx.counters()["tma_gemm_launches"] == before + 1, "TMA kernel was not used"
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(k)
+    ctx.set_option("disable_tma", 1)
+    try:
+        rng = np.random.default_rng(m + n + k)
+        got2, _ = _gemm(tk, ctx, "T", "N", m, n, k, rng, alpha, beta)
+    finally:
+        ctx.set_option("disable_tma", 0)
+    assert ctx.counters()["tma_gemm_launches"] == before + 1
+    assert np.abs(got - got2).max() <= 1e-12 * max(1.0, np.abs(ref).max())

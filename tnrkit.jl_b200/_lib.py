@@ -27,6 +27,8 @@ _SIGNATURES = {
     "tnr_get_counters": [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                          C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnr_reset_counters": [C.c_void_p],
+    "tnr_get_tma_launches": [C.c_void_p, C.POINTER(C.c_uint64)],
+    "tnr_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
     "tnr_gemm_timing": [C.c_void_p, C.c_int],
     "tnr_gemm_timing_read": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _c_i64p],
     "tnr_malloc": [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)],
@@ -125,8 +127,13 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         f, pb = C.c_double(), C.c_double()
         self.call("tnr_get_counters", C.byref(a), C.byref(b), C.byref(f), C.byref(pb))
+        t = C.c_uint64()
+        self.call("tnr_get_tma_launches", C.byref(t))
         return {"launches": a.value, "gemm_launches": b.value, "gemm_flops": f.value,
-                "permute_bytes": pb.value}
+                "permute_bytes": pb.value, "tma_gemm_launches": t.value}
+
+    def set_option(self, key: str, value: int):
+        self.call("tnr_set_option", key.encode(), int(value))
 
     def reset_counters(self):
         self.call("tnr_reset_counters")

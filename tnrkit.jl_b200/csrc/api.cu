@@ -127,6 +127,20 @@ int tnr_reset_counters(tnr_context* ctx) {
     return 0;
 }
 
+int tnr_get_tma_launches(tnr_context* ctx, uint64_t* n) {
+    if (!ctx || !n) return 1;
+    *n = ctx->c.ctr.tma_gemm_launches;
+    return 0;
+}
+
+int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return 1;
+    return guard(ctx, [&] {
+        if (std::strcmp(key, "disable_tma") == 0) ctx->c.disable_tma = value != 0;
+        else throw Error(1, std::string("unknown option: ") + key);
+    });
+}
+
 int tnr_gemm_timing(tnr_context* ctx, int enable) {
     if (!ctx) return 1;
     return guard(ctx, [&] {

@@ -33,6 +33,7 @@ struct Error : std::runtime_error {
 struct Counters {
     unsigned long long launches = 0;       // all kernels of this library
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
+    unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
     double permute_bytes = 0.0;            // read+write bytes moved by permute kernels
 };
@@ -45,6 +46,7 @@ struct Context {
     Counters ctr;
     // optional timing of the big GEMM (dominant kernel) with events on ctx->stream
     bool time_gemm = false;
+    bool disable_tma = false;  // force the cp.async GEMM (A/B testing)
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     std::string last_error;
@@ -67,6 +69,11 @@ struct GemmBatch {
 void gemm(Context* ctx, char transa, char transb, int m, int n, int k, double alpha,
           const double* A, long long lda, const double* B, long long ldb, double beta,
           double* C, long long ldc, const GemmBatch& batch = GemmBatch());
+
+// gemm_tma.cu: warp-specialised TMA + mbarrier + DMMA kernel for the TN layout; returns false
+// when the problem does not fit (caller falls back to the cp.async kernel)
+bool gemm_tma_tn(Context* ctx, int m, int n, int k, double alpha, const double* A, long long lda,
+                 const double* B, long long ldb, double beta, double* C, long long ldc);
 
 // ---- kernels: permute.cu ----
 // dst[sum i_j*dstride_j] = src[sum i_j*sstride_j] for all multi-indices i < dims.

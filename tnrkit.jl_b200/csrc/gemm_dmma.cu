@@ -59,46 +59,73 @@ struct GemmParams {
     int a16, b16, c16; // 16-byte alignment flags
 };
 
-// Loads one BMxBK (or BNxBK) operand tile.  KC: K is the contiguous dimension in global.
+// Per-thread loader state for one operand tile (BR rows x BK).  Each thread owns
+// PER_THREAD 16-byte chunks whose row / k position inside the tile never changes; only the
+// k-tile base advances.  KC: K is the contiguous dimension in global memory.
 template <int BR, bool KC>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long long ld,
-                                          int r0, int k0, int R, int Kend, bool al16) {
-    constexpr int CHUNKS = BR * BK / 2;
-    constexpr int PER_THREAD = CHUNKS / NTHREADS;
+struct TileLoader {
+    static constexpr int CHUNKS = BR * BK / 2;
+    static constexpr int PER_THREAD = (CHUNKS + NTHREADS - 1) / NTHREADS;
+    const double* g[PER_THREAD];   // global address of the chunk in k-tile 0 (row/k offset applied)
+    int soff[PER_THREAD];          // shared offset (doubles) inside a stage
+    int kin[PER_THREAD];           // k offset of the chunk inside the tile
+    int rvalid[PER_THREAD];        // KC: 2 if row valid else 0 ; !KC: valid elements along rows (0..2)
+    const double* base;
+    long long kstride;             // global advance per k-tile (doubles)
+    bool al16;
+
+    __device__ __forceinline__ void init(const double* gbase, long long ld, int r0, int kbeg, int R,
+                                         bool aligned) {
+        base = gbase;
+        al16 = aligned;
+        kstride = KC ? (long long)BK : (long long)BK * ld;
 #pragma unroll
-    for (int it = 0; it < PER_THREAD; ++it) {
-        int c = threadIdx.x + it * NTHREADS;
-        int r, k;
-        double* sp;
-        if (KC) {
-            r = c / (BK / 2);
-            k = (c % (BK / 2)) * 2;
-            sp = s + r * (BK + PADK) + k;
-        } else {
-            k = c / (BR / 2);
-            r = (c % (BR / 2)) * 2;
-            sp = s + k * (BR + PADM) + r;
+        for (int it = 0; it < PER_THREAD; ++it) {
+            int c = threadIdx.x + it * NTHREADS;
+            int r, k;
+            if (KC) {
+                r = c / (BK / 2);
+                k = (c % (BK / 2)) * 2;
+                soff[it] = r * (BK + PADK) + k;
+            } else {
+                k = c / (BR / 2);
+                r = (c % (BR / 2)) * 2;
+                soff[it] = k * (BR + PADM) + r;
+            }
+            if (CHUNKS % NTHREADS != 0 && c >= CHUNKS) {  // thread has no chunk in this slot
+                rvalid[it] = -1;
+                g[it] = gbase;
+                kin[it] = 0;
+                continue;
+            }
+            int gr = r0 + r;
+            kin[it] = k;
+            if (KC) {
+                rvalid[it] = (gr < R) ? 2 : 0;
+                g[it] = gbase + (long long)gr * ld + kbeg + k;
+            } else {
+                rvalid[it] = max(0, min(2, R - gr));
+                g[it] = gbase + (long long)(kbeg + k) * ld + gr;
+            }
         }
-        int gr = r0 + r, gk = k0 + k;
-        // number of valid elements among the 2 of this chunk
+    }
+
+    // issue chunk slot `it` of k-tile `kt` (tile-relative), krem = kend - k0 of this tile
+    __device__ __forceinline__ void issue(double* stage, int it, int kt, int krem) const {
+        if (rvalid[it] < 0) return;
         int valid;
-        const double* gp;
-        if (KC) {
-            valid = (gr < R) ? max(0, min(2, Kend - gk)) : 0;
-            gp = g + (long long)gr * ld + gk;
-        } else {
-            valid = (gk < Kend) ? max(0, min(2, R - gr)) : 0;
-            gp = g + (long long)gk * ld + gr;
-        }
-        if (valid == 0) gp = g;
+        if (KC) valid = min(rvalid[it], max(0, krem - kin[it]));
+        else valid = (kin[it] < krem) ? rvalid[it] : 0;
+        const double* gp = valid ? g[it] + kt * kstride : base;
+        double* sp = stage + soff[it];
         if (al16) {
             cp_async16(sp, gp, valid * 8);
         } else {
             cp_async8(sp, gp, valid >= 1 ? 8 : 0);
-            cp_async8(sp + 1, valid >= 2 ? gp + 1 : g, valid >= 2 ? 8 : 0);
+            cp_async8(sp + 1, valid >= 2 ? gp + 1 : base, valid >= 2 ? 8 : 0);
         }
     }
-}
+};
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool KA, bool KB, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams p) {
@@ -142,24 +169,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto issue = [&](int kt) {
+    TileLoader<BM, KA> la;
+    TileLoader<BN, KB> lb;
+    la.init(A, p.lda, m0, kbeg, p.M, p.a16);
+    lb.init(B, p.ldb, n0, kbeg, p.N, p.b16);
+    constexpr int PTA = TileLoader<BM, KA>::PER_THREAD, PTB = TileLoader<BN, KB>::PER_THREAD;
+
+    // part q (0..3) of the loads of k-tile kt: interleaved with the four k4-steps of the
+    // tile being computed so the DMMA pipe never waits behind a block of address arithmetic
+    auto issue_part = [&](int kt, int q) {
         if (kt < KT) {
             double* sa = smem + (kt % STAGES) * STAGE;
             double* sb = sa + A_STAGE;
-            int k0 = kbeg + kt * BK;
-            load_tile<BM, KA>(sa, A, p.lda, m0, k0, p.M, kend, p.a16);
-            load_tile<BN, KB>(sb, B, p.ldb, n0, k0, p.N, kend, p.b16);
+            int krem = (kend - kbeg) - kt * BK;
+#pragma unroll
+            for (int it = 0; it < PTA; ++it)
+                if (it % 4 == q) la.issue(sa, it, kt, krem);
+#pragma unroll
+            for (int it = 0; it < PTB; ++it)
+                if (it % 4 == q) lb.issue(sb, it, kt, krem);
         }
-        cp_async_commit();
     };
 
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    for (int s = 0; s < STAGES - 1; ++s) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) issue_part(s, q);
+        cp_async_commit();
+    }
 
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        issue(kt + STAGES - 1);
         const double* sa = smem + (kt % STAGES) * STAGE;
         const double* sb = sa + A_STAGE;
 #pragma unroll
@@ -175,11 +216,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams
                 int c = wn * WTN + 8 * j + lr, k = kk * 4 + lc;
                 bf[j] = KB ? sb[c * (BK + PADK) + k] : sb[k * (BN + PADM) + c];
             }
+            issue_part(kt + STAGES - 1, kk);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -338,7 +381,10 @@ void gemm(Context* ctx, char transa, char transb, int m, int n, int k, double al
         TNR_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     // KA: A is K-contiguous (transa == 'T');  KB: B is K-contiguous (transb == 'N')
-    if (ta && !tb) launch_layout<true, true>(ctx, p, nbatch);
+    if (ta && !tb && nbatch == 1 &&
+        gemm_tma_tn(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)) {
+        // handled by the TMA kernel
+    } else if (ta && !tb) launch_layout<true, true>(ctx, p, nbatch);
     else if (ta && tb) launch_layout<true, false>(ctx, p, nbatch);
     else if (!ta && !tb) launch_layout<false, true>(ctx, p, nbatch);
     else launch_layout<false, false>(ctx, p, nbatch);

@@ -5,6 +5,9 @@ import torch
 import tnrkit.jl_b200 as tk
 
 ctx = tk.default_context()
+if os.environ.get("TNR_DISABLE_TMA"):
+    ctx.set_option("disable_tma", 1)
+    print("TMA kernel disabled (cp.async kernel for every layout)")
 shapes = [("T", "N", 13824, 13824, 13824), ("T", "N", 6144, 6144, 13824), ("T", "N", 4096, 4096, 4096),
           ("T", "N", 576, 576, 331776), ("N", "N", 7962624 // 4, 576 // 4 * 4, 24), ("N", "N", 8192, 8192, 8192),
           ("N", "T", 8192, 8192, 8192), ("T", "T", 8192, 8192, 8192)]
