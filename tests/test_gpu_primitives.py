@@ -128,7 +128,7 @@ def test_eigh_trunc(tk, n, chi):
     assert np.abs(mm @ v - v * w).max() <= 1e-11 * scale
 
 
-@pytest.mark.parametrize("m,n,k,alpha,beta", [(1664, 1664, 96, 1.0, 0.0), (1601, 1555, 77, -0.5, 2.0),
+@pytest.mark.parametrize("m,n,k,alpha,beta", [(1664, 1664, 96, 1.0, 0.0), (1601, 1555, 78, -0.5, 2.0),
                                               (2048, 1536, 1000, 1.0, 0.0), (1538, 1666, 64, 2.0, 1.0)])
 def test_gemm_tma_path(tk, ctx, m, n, k, alpha, beta):
     """TN problems with >= 148 tiles take the TMA/mbarrier kernel (ragged edges are zero
@@ -146,3 +146,13 @@ def test_gemm_tma_path(tk, ctx, m, n, k, alpha, beta):
         ctx.set_option("disable_tma", 0)
     assert ctx.counters()["tma_gemm_launches"] == before + 1
     assert np.abs(got - got2).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_gemm_tma_fallback_on_odd_leading_dimension(tk, ctx):
+    """K = 77 gives an odd leading dimension (row stride not a multiple of 16 bytes): TMA cannot
+    describe it, the cp.async kernel takes over and the result is still right."""
+    rng = np.random.default_rng(9)
+    before = ctx.counters()["tma_gemm_launches"]
+    got, ref = _gemm(tk, ctx, "T", "N", 1601, 1555, 77, rng)
+    assert ctx.counters()["tma_gemm_launches"] == before
+    assert np.abs(got - ref).max() <= 1e-11
