@@ -302,8 +302,10 @@ def run_gpu(args):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "kernel": "gemm_dmma_kernel<128,128,2,4,KA,KB,4> (chunked chi^3 x chi^3 x chi^3 "
-                          "contraction)", "launches_timed": gemm_n,
+                "kernel": "gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
+                          "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
+                          "projector Gram GEMMs above 1e11 flop)", "launches_timed": gemm_n,
+                "tma_gemm_launches": ctr.get("tma_gemm_launches"),
                 "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (of measured; "
                                "MEASURED_PEAKS.json holds no FP64 figure); nominal FP64 tensor "
                                "peak 40 TFLOP/s",

@@ -72,10 +72,49 @@ int tnr_gemm_strided_batched(tnr_context* ctx, char transa, char transb, int m, 
                              double alpha, const double* A, int64_t lda, int64_t strideA,
                              const double* B, int64_t ldb, int64_t strideB, double beta,
                              double* C, int64_t ldc, int64_t strideC, int batch);
+/* Grouped GEMM: `count` independent problems C_g = alpha op(A_g) op(B_g) + beta C_g in ONE
+ * launch -- the per-coupled-sector block products of a Z2 / ZN / U1 block-sparse contraction
+ * (TensorKit `mul!` loops over `blocks(t)`; e.g. the per-sector products behind every
+ * `@tensor` line of src/schemes/trg.jl:42 and btrg.jl:86-94 for `Z2Irrep` / `ZNIrrep` tensors). */
+typedef struct {
+    int32_t m, n, k;
+    const double* A;
+    int64_t lda;
+    const double* B;
+    int64_t ldb;
+    double* C;
+    int64_t ldc;
+} tnr_gemm_problem;
+int tnr_gemm_grouped(tnr_context* ctx, char transa, char transb, int count,
+                     const tnr_gemm_problem* problems, double alpha, double beta);
 /* dst leg k = src leg perm[k] (0-based); replaces TensorKit.permute / transpose
  * (src/schemes/hotrg3d.jl:134, atrg.jl:40, atrg3d.jl:37, trg.jl:40). */
 int tnr_permute(tnr_context* ctx, const double* src, double* dst, int rank, const int64_t* dims,
                 const int* perm);
+/* dst[sum_j i_j*dstride_j] = src[sum_j i_j*sstride_j] for all 0 <= i_j < dims[j]: block
+ * gather/scatter between the tuple blocks and the coupled-sector matrices of an abelian
+ * symmetric tensor (TensorKit's fusion-tree block <-> matrix-block views, `permute` on
+ * `Z2Irrep` / `ZNIrrep` tensors). */
+int tnr_strided_copy(tnr_context* ctx, const double* src, double* dst, int rank,
+                     const int64_t* dims, const int64_t* sstride, const int64_t* dstride);
+/* sum over the multi-index of w_0[i_0]..w_r[i_r] * src[sum_j i_j*stride_j] (weights may be
+ * NULL): partial traces `@tensor T[1 2; 2 1]` of finalize! on one block
+ * (src/utility/finalize.jl:4-14).  rank <= 4.  Result returned to the host. */
+int tnr_strided_sum(tnr_context* ctx, const double* src, int rank, const int64_t* dims,
+                    const int64_t* stride, const double* const* weights, double* sum_out);
+/* x *= alpha  (`scheme.T /= n`, finalize.jl:6) */
+int tnr_scale(tnr_context* ctx, double* x, int64_t n, double alpha);
+/* A(m x n, lda): rows ? A[i,:] *= f(s[i]) : A[:,j] *= f(s[j]); f = identity (mode 0),
+ * sqrt (mode 1: `U * sqrt(S)`, projectors.jl:218) or pseudopow(.,p) (mode 2: btrg.jl:51-60) */
+int tnr_diag_scale(tnr_context* ctx, double* A, int64_t m, int64_t n, int64_t lda, const double* s,
+                   int rows, int mode, double p);
+/* out[i] = f(s[i]) with the same modes (S_b = pseudopow(S, k), btrg.jl:66) */
+int tnr_vec_map(tnr_context* ctx, const double* s, double* out, int64_t n, int mode, double p);
+/* Sector-global truncrank on the device: rank[j] = position of |vals[j]| in descending order
+ * over the concatenated spectra of all sectors, eps = 2-norm of the values of rank >= k.
+ * Only the n ranks travel to the host (block shapes are host metadata). */
+int tnr_topk_select(tnr_context* ctx, const double* vals, int64_t n, int64_t k, int32_t* rank_host,
+                    double* eps_out);
 /* Pairwise contraction by single-character leg labels (einsum for two operands; labels that
  * appear in A and B but not in C are summed).  Replaces one binary `@tensor` contraction
  * (TensorOperations.tensorcontract!).  C is written compact in label order labelsC. */

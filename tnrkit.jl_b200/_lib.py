@@ -18,6 +18,13 @@ _c_i64p = C.POINTER(C.c_int64)
 _c_dp = C.c_void_p  # raw device pointers travel as integers
 
 # name -> (argtypes)  ; every function returns int except where noted
+class GemmProblem(C.Structure):
+    """tnr_gemm_problem"""
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("A", C.c_void_p),
+                ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p),
+                ("ldc", C.c_int64)]
+
+
 _SIGNATURES = {
     "tnr_version": [],
     "tnr_create": [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)],
@@ -40,7 +47,18 @@ _SIGNATURES = {
     "tnr_gemm_strided_batched": [C.c_void_p, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int,
                                  C.c_double, _c_dp, C.c_int64, C.c_int64, _c_dp, C.c_int64,
                                  C.c_int64, C.c_double, _c_dp, C.c_int64, C.c_int64, C.c_int],
+    "tnr_gemm_grouped": [C.c_void_p, C.c_char, C.c_char, C.c_int, C.POINTER(GemmProblem),
+                         C.c_double, C.c_double],
     "tnr_permute": [C.c_void_p, _c_dp, _c_dp, C.c_int, _c_i64p, C.POINTER(C.c_int)],
+    "tnr_strided_copy": [C.c_void_p, _c_dp, _c_dp, C.c_int, _c_i64p, _c_i64p, _c_i64p],
+    "tnr_strided_sum": [C.c_void_p, _c_dp, C.c_int, _c_i64p, _c_i64p, C.POINTER(C.c_void_p),
+                        C.POINTER(C.c_double)],
+    "tnr_scale": [C.c_void_p, _c_dp, C.c_int64, C.c_double],
+    "tnr_diag_scale": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.c_int64, _c_dp, C.c_int, C.c_int,
+                       C.c_double],
+    "tnr_vec_map": [C.c_void_p, _c_dp, _c_dp, C.c_int64, C.c_int, C.c_double],
+    "tnr_topk_select": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.POINTER(C.c_int32),
+                        C.POINTER(C.c_double)],
     "tnr_contract": [C.c_void_p, _c_dp, C.c_int, _c_i64p, C.c_char_p, _c_dp, C.c_int, _c_i64p,
                      C.c_char_p, _c_dp, C.c_char_p],
     "tnr_svd_trunc": [C.c_void_p, _c_dp, C.c_int, _c_i64p, C.c_int, C.c_int, _c_dp, _c_dp, _c_dp,

@@ -228,6 +228,20 @@ int tnr_gemm_strided_batched(tnr_context* ctx, char transa, char transb, int m, 
     });
 }
 
+int tnr_gemm_grouped(tnr_context* ctx, char transa, char transb, int count,
+                     const tnr_gemm_problem* problems, double alpha, double beta) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(count >= 0 && (count == 0 || problems), "gemm_grouped: bad arguments");
+        std::vector<GroupedProblem> v(count);
+        for (int g = 0; g < count; ++g) {
+            const tnr_gemm_problem& q = problems[g];
+            v[g] = GroupedProblem{q.m, q.n, q.k, q.A, q.lda, q.B, q.ldb, q.C, q.ldc};
+        }
+        gemm_grouped(&ctx->c, transa, transb, v, alpha, beta);
+    });
+}
+
 int tnr_permute(tnr_context* ctx, const double* src, double* dst, int rank, const int64_t* dims,
                 const int* perm) {
     if (!ctx) return 1;
@@ -448,6 +462,74 @@ int tnr_finalize_3d(tnr_context* ctx, double* T, const int64_t* dims, double* no
         DT t = in_view(&ctx->c, T, to_dims(dims, 6));
         double n = finalize_3d(&ctx->c, t);
         if (norm_out) *norm_out = n;
+    });
+}
+
+}  // extern "C"
+
+// ---- small primitives used by the block-sparse (abelian sector) host layer ----
+extern "C" {
+
+int tnr_strided_copy(tnr_context* ctx, const double* src, double* dst, int rank,
+                     const int64_t* dims, const int64_t* sstride, const int64_t* dstride) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(rank >= 0 && rank <= 16 && dims && sstride && dstride, "strided_copy: bad args");
+        long long d[16], ss[16], ds[16];
+        for (int i = 0; i < rank; ++i) { d[i] = dims[i]; ss[i] = sstride[i]; ds[i] = dstride[i]; }
+        strided_copy(&ctx->c, src, dst, rank, d, ss, ds);
+    });
+}
+
+int tnr_strided_sum(tnr_context* ctx, const double* src, int rank, const int64_t* dims,
+                    const int64_t* stride, const double* const* weights, double* sum_out) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(rank >= 1 && rank <= 4 && dims && stride && sum_out, "strided_sum: bad args");
+        long long d[4], st[4];
+        for (int i = 0; i < rank; ++i) { d[i] = dims[i]; st[i] = stride[i]; }
+        DT out(&ctx->c, {1});
+        strided_sum_w(&ctx->c, src, rank, d, st, weights, out.p, false);
+        TNR_CUDA(cudaMemcpyAsync(sum_out, out.p, 8, cudaMemcpyDeviceToHost, ctx->c.stream));
+        TNR_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    });
+}
+
+int tnr_scale(tnr_context* ctx, double* x, int64_t n, double alpha) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] { scale(&ctx->c, x, n, alpha); });
+}
+
+int tnr_diag_scale(tnr_context* ctx, double* A, int64_t m, int64_t n, int64_t lda, const double* s,
+                   int rows, int mode, double p) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(mode >= 0 && mode <= 2, "diag_scale: mode must be 0 (s), 1 (sqrt s), 2 (pseudopow)");
+        diag_scale(&ctx->c, A, m, n, lda, s, rows != 0, mode, p);
+    });
+}
+
+int tnr_vec_map(tnr_context* ctx, const double* s, double* out, int64_t n, int mode, double p) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] { vec_map(&ctx->c, s, out, n, mode, p); });
+}
+
+int tnr_topk_select(tnr_context* ctx, const double* vals, int64_t n, int64_t k, int32_t* rank_host,
+                    double* eps_out) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(n >= 1 && k >= 0 && rank_host, "topk_select: bad args");
+        int* d_rank = nullptr;
+        TNR_CUDA(cudaMallocAsync((void**)&d_rank, n * sizeof(int), ctx->c.stream));
+        DT eps(&ctx->c, {1});
+        rank_select(&ctx->c, vals, n, k, d_rank, eps.p);
+        double e = 0.0;
+        TNR_CUDA(cudaMemcpyAsync(rank_host, d_rank, n * sizeof(int), cudaMemcpyDeviceToHost,
+                                 ctx->c.stream));
+        TNR_CUDA(cudaMemcpyAsync(&e, eps.p, 8, cudaMemcpyDeviceToHost, ctx->c.stream));
+        TNR_CUDA(cudaStreamSynchronize(ctx->c.stream));
+        TNR_CUDA(cudaFreeAsync(d_rank, ctx->c.stream));
+        if (eps_out) *eps_out = e;
     });
 }
 

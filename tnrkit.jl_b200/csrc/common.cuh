@@ -33,6 +33,7 @@ struct Error : std::runtime_error {
 struct Counters {
     unsigned long long launches = 0;       // all kernels of this library
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
+    unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
     double permute_bytes = 0.0;            // read+write bytes moved by permute kernels
@@ -69,6 +70,19 @@ struct GemmBatch {
 void gemm(Context* ctx, char transa, char transb, int m, int n, int k, double alpha,
           const double* A, long long lda, const double* B, long long ldb, double beta,
           double* C, long long ldc, const GemmBatch& batch = GemmBatch());
+
+// grouped launch: independent problems (per-sector blocks) sharing op(A), op(B), alpha, beta
+struct GroupedProblem {
+    int m, n, k;
+    const double* A;
+    long long lda;
+    const double* B;
+    long long ldb;
+    double* C;
+    long long ldc;
+};
+void gemm_grouped(Context* ctx, char transa, char transb, const std::vector<GroupedProblem>& probs,
+                  double alpha, double beta);
 
 // gemm_tma.cu: warp-specialised TMA + mbarrier + DMMA kernel for the TN layout; returns false
 // when the problem does not fit (caller falls back to the cp.async kernel)

@@ -128,7 +128,8 @@ struct TileLoader {
 };
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool KA, bool KB, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+__device__ __forceinline__ void gemm_body(const GemmParams& p, const int tile_id, const int split,
+                                          const int b) {
     constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
     constexpr int MI = WTM / 8, NJ = WTN / 8;
     constexpr int A_STAGE = KA ? BM * (BK + PADK) : BK * (BM + PADM);
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams
 
     // ---- tile coordinates (grouped ordering for L2 reuse) ----
     const int GROUP = 8;
-    int t = blockIdx.x;
+    int t = tile_id;
     int per_group = GROUP * p.tiles_n;
     int group_id = t / per_group;
     int first_m = group_id * GROUP;
@@ -149,12 +150,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams
     int tn = (t % per_group) / gsize;
     const int m0 = tm * BM, n0 = tn * BN;
 
-    const int split = blockIdx.y;
     const int kbeg = split * p.k_per_split;
     const int kend = min(p.K, kbeg + p.k_per_split);
     const int KT = (kend - kbeg + BK - 1) / BK;
 
-    const int b = blockIdx.z;
     const int b1 = b % p.nb1, b2 = b / p.nb1;
     const double* __restrict__ A = p.A + b1 * p.sA1 + b2 * p.sA2;
     const double* __restrict__ B = p.B + b1 * p.sB1 + b2 * p.sB2;
@@ -279,6 +278,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams
     }
 }
 
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool KA, bool KB, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_dmma_kernel(const GemmParams p) {
+    gemm_body<BM, BN, WARPS_M, WARPS_N, KA, KB, STAGES>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Grouped launch: one kernel covers `nprob` independent problems (the per-sector blocks of a
+// symmetric contraction); CTA -> problem through the tile prefix table.
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool KA, bool KB, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_dmma_grouped_kernel(const GemmParams* __restrict__ table, const int* __restrict__ tile_start,
+                         int nprob) {
+    __shared__ GemmParams sp;
+    __shared__ int s_first;
+    if (threadIdx.x == 0) {
+        int g = 0;
+        while (g + 1 < nprob && tile_start[g + 1] <= (int)blockIdx.x) ++g;
+        sp = table[g];
+        s_first = tile_start[g];
+    }
+    __syncthreads();
+    gemm_body<BM, BN, WARPS_M, WARPS_N, KA, KB, STAGES>(sp, blockIdx.x - s_first, 0, 0);
+}
+
 __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int splits, long long mn,
                                      int M, double* __restrict__ C, long long ldc, double alpha,
                                      double beta) {
@@ -394,6 +416,92 @@ void gemm(Context* ctx, char transa, char transb, int m, int n, int k, double al
         ctx->timed_flops += 2.0 * m * n * (double)k * nbatch;
     }
     ctx->ctr.gemm_flops += 2.0 * m * n * (double)k * nbatch;
+}
+
+}  // namespace tnr
+
+// ---------------------------------------------------------------------------
+// grouped GEMM: all per-sector blocks of a symmetric (Z2/ZN/U1 block-sparse) contraction in
+// ONE launch.  Problems share op(A)/op(B) and alpha/beta; sizes and pointers are per problem.
+// ---------------------------------------------------------------------------
+namespace tnr {
+namespace {
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool KA, bool KB>
+void launch_grouped_cfg(Context* ctx, std::vector<GemmParams>& tab) {
+    constexpr int STAGES = 4;
+    constexpr int A_STAGE = KA ? BM * (BK + PADK) : BK * (BM + PADM);
+    constexpr int B_STAGE = KB ? BN * (BK + PADK) : BK * (BN + PADM);
+    constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    auto kern = gemm_dmma_grouped_kernel<BM, BN, WARPS_M, WARPS_N, KA, KB, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        TNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        configured = true;
+    }
+    std::vector<int> start(tab.size() + 1, 0);
+    for (size_t g = 0; g < tab.size(); ++g) {
+        GemmParams& p = tab[g];
+        p.tiles_m = (p.M + BM - 1) / BM;
+        p.tiles_n = (p.N + BN - 1) / BN;
+        p.splits = 1;
+        p.k_per_split = ((p.K + BK - 1) / BK) * BK;
+        p.partial = nullptr;
+        start[g + 1] = start[g] + p.tiles_m * p.tiles_n;
+    }
+    GemmParams* d_tab = nullptr;
+    int* d_start = nullptr;
+    TNR_CUDA(cudaMallocAsync((void**)&d_tab, tab.size() * sizeof(GemmParams), ctx->stream));
+    TNR_CUDA(cudaMallocAsync((void**)&d_start, start.size() * sizeof(int), ctx->stream));
+    TNR_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(GemmParams),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    TNR_CUDA(cudaMemcpyAsync(d_start, start.data(), start.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    // pageable sources: the copies above are complete w.r.t. the host buffers on return
+    kern<<<(unsigned)start.back(), NTHREADS, SMEM, ctx->stream>>>(d_tab, d_start, (int)tab.size());
+    TNR_CUDA(cudaGetLastError());
+    TNR_CUDA(cudaFreeAsync(d_tab, ctx->stream));
+    TNR_CUDA(cudaFreeAsync(d_start, ctx->stream));
+    ctx->ctr.launches++;
+    ctx->ctr.gemm_launches++;
+    ctx->ctr.grouped_gemm_launches++;
+}
+
+template <bool KA, bool KB>
+void launch_grouped_layout(Context* ctx, std::vector<GemmParams>& tab, bool narrow) {
+    if (narrow) launch_grouped_cfg<256, 32, 8, 1, KA, KB>(ctx, tab);
+    else launch_grouped_cfg<128, 128, 2, 4, KA, KB>(ctx, tab);
+}
+
+}  // namespace
+
+void gemm_grouped(Context* ctx, char transa, char transb, const std::vector<GroupedProblem>& probs,
+                  double alpha, double beta) {
+    bool ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+    std::vector<GemmParams> tab;
+    bool narrow = true;
+    auto even = [](long long x) { return (x & 1LL) == 0; };
+    for (const GroupedProblem& q : probs) {
+        if (q.m <= 0 || q.n <= 0) continue;
+        TNR_CHECK(q.k > 0, "gemm_grouped: k must be positive");
+        GemmParams p{};
+        p.A = q.A; p.B = q.B; p.C = q.C;
+        p.lda = q.lda; p.ldb = q.ldb; p.ldc = q.ldc;
+        p.M = q.m; p.N = q.n; p.K = q.k;
+        p.alpha = alpha; p.beta = beta;
+        p.nb1 = 1;
+        p.a16 = ((uintptr_t)q.A % 16 == 0) && even(q.lda);
+        p.b16 = ((uintptr_t)q.B % 16 == 0) && even(q.ldb);
+        p.c16 = ((uintptr_t)q.C % 16 == 0) && even(q.ldc);
+        narrow = narrow && (q.n <= 48);
+        tab.push_back(p);
+        ctx->ctr.gemm_flops += 2.0 * q.m * q.n * (double)q.k;
+    }
+    if (tab.empty()) return;
+    if (ta && !tb) launch_grouped_layout<true, true>(ctx, tab, narrow);
+    else if (ta && tb) launch_grouped_layout<true, false>(ctx, tab, narrow);
+    else if (!ta && !tb) launch_grouped_layout<false, true>(ctx, tab, narrow);
+    else launch_grouped_layout<false, false>(ctx, tab, narrow);
 }
 
 }  // namespace tnr

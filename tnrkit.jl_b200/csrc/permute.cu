@@ -27,13 +27,18 @@ struct CopyParams {
     long long ni, si_s, si_d;  // src-fastest dim: extent, src stride, dst stride
     long long nj, sj_s, sj_d;  // dst-fastest dim
     long long tiles_i, tiles_j;
+    int ti, tj;                // tile extents along i and j
     long long total;           // total elements (row kernel)
 };
+
+// Tile extents adapt to short legs: a leg of extent <= 48 (bond dimension chi = 24, 32, 48)
+// is taken whole, so every lane moves data and every 32-byte sector is fully used.
+constexpr int TMAX = 48;
 
 __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restrict__ src,
                                                          double* __restrict__ dst,
                                                          const CopyParams p) {
-    __shared__ double tile[32][33];
+    __shared__ double tile[TMAX * (TMAX + 1)];
     long long bid = blockIdx.x;
     long long ti = bid % p.tiles_i;
     bid /= p.tiles_i;
@@ -49,22 +54,22 @@ __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restric
             doff += i * p.ds[d];
         }
     }
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    long long i0 = ti * 32, j0 = tj * 32;
-    // read: tx along i (src contiguous), rows along j
-    long long i = i0 + tx;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        long long j = j0 + ty + 8 * r;
-        if (i < p.ni && j < p.nj) tile[ty + 8 * r][tx] = src[soff + i * p.si_s + j * p.sj_s];
+    const int TI = p.ti, TJ = p.tj;
+    const long long i0 = ti * TI, j0 = tj * TJ;
+    const int ni = (int)min((long long)TI, p.ni - i0), nj = (int)min((long long)TJ, p.nj - j0);
+    const int count = ni * nj;
+    const double* sp = src + soff + i0 * p.si_s + j0 * p.sj_s;
+    double* dp = dst + doff + i0 * p.si_d + j0 * p.sj_d;
+    // read: i fastest (src contiguous)
+    for (int idx = threadIdx.x; idx < count; idx += 256) {
+        int i = idx % ni, j = idx / ni;
+        tile[j * (TMAX + 1) + i] = sp[i * p.si_s + j * p.sj_s];
     }
     __syncthreads();
-    // write: tx along j (dst contiguous), rows along i
-    long long j = j0 + tx;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        long long ii = i0 + ty + 8 * r;
-        if (ii < p.ni && j < p.nj) dst[doff + ii * p.si_d + j * p.sj_d] = tile[tx][ty + 8 * r];
+    // write: j fastest (dst contiguous)
+    for (int idx = threadIdx.x; idx < count; idx += 256) {
+        int j = idx % nj, i = idx / nj;
+        dp[i * p.si_d + j * p.sj_d] = tile[j * (TMAX + 1) + i];
     }
 }
 
@@ -165,8 +170,10 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
             p.rank++;
             outer *= m[i].n;
         }
-        p.tiles_i = (p.ni + 31) / 32;
-        p.tiles_j = (p.nj + 31) / 32;
+        p.ti = p.ni <= TMAX ? (int)p.ni : 32;
+        p.tj = p.nj <= TMAX ? (int)p.nj : 32;
+        p.tiles_i = (p.ni + p.ti - 1) / p.ti;
+        p.tiles_j = (p.nj + p.tj - 1) / p.tj;
         long long blocks = p.tiles_i * p.tiles_j * outer;
         TNR_CHECK(blocks < (1LL << 31), "strided_copy: grid too large");
         copy_tiled_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, dst, p);
