@@ -48,6 +48,9 @@ int tnr_get_counters(tnr_context* ctx, uint64_t* launches, uint64_t* gemm_launch
 int tnr_reset_counters(tnr_context* ctx);
 /* counters of the warp-specialised TMA GEMM (subset of gemm_launches) */
 int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
+/* any counter by name: "launches", "gemm_launches", "grouped_gemm_launches",
+ * "tma_gemm_launches", "gemm_flops", "permute_bytes" */
+int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
 /* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests) */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
@@ -108,6 +111,10 @@ int tnr_scale(tnr_context* ctx, double* x, int64_t n, double alpha);
  * sqrt (mode 1: `U * sqrt(S)`, projectors.jl:218) or pseudopow(.,p) (mode 2: btrg.jl:51-60) */
 int tnr_diag_scale(tnr_context* ctx, double* A, int64_t m, int64_t n, int64_t lda, const double* s,
                    int rows, int mode, double p);
+/* A viewed as [m1][n][m2] (column major): A[i,j,k] *= f(s[j]) -- a diagonal bond tensor applied
+ * to any leg (the S1 / S2 factors of the BTRG contraction, btrg.jl:86-94) */
+int tnr_axis_scale(tnr_context* ctx, double* A, int64_t m1, int64_t n, int64_t m2, const double* s,
+                   int mode, double p);
 /* out[i] = f(s[i]) with the same modes (S_b = pseudopow(S, k), btrg.jl:66) */
 int tnr_vec_map(tnr_context* ctx, const double* s, double* out, int64_t n, int mode, double p);
 /* Sector-global truncrank on the device: rank[j] = position of |vals[j]| in descending order

@@ -7,13 +7,14 @@ interface for that path: scheme constructors, `run!`, `truncrank`, `maxiter`,
 from . import _lib
 from ._lib import Context, TNRCudaError, default_context
 from .free_energy import free_energy
-from .models import (Trivial, Z2Irrep, ZNIrrep, classical_ising, classical_ising_3D,
+from .models import (ChargedArray, Trivial, Z2Irrep, ZNIrrep, classical_ising, classical_ising_3D,
                      classical_potts, f_onsager, ising_bc, ising_bc_3D, ising_βc, ising_βc_3D,
                      potts_bc, potts_βc)
 from .schemes import (ATRG, ATRG_3D, BTRG, HOTRG, HOTRG_3D, TRG, Finalizer, TNRScheme,
                       allgather_last_leg, beta_sweep, default_Finalizer, finalize, run, run_,
                       shard_range)
 from .stopping import MultipleCrit, convcrit, maxiter, stopcrit, trivial_convcrit
+from .symmetric import Leg, SymTensor, sym_contract, sym_svd_trunc
 from .tensor import DeviceTensor, contract, eigh_trunc, svd_trunc
 from .truncation import truncrank, trunctol
 

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "tnr_reset_counters": [C.c_void_p],
     "tnr_get_tma_launches": [C.c_void_p, C.POINTER(C.c_uint64)],
     "tnr_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
+    "tnr_get_counter": [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)],
     "tnr_gemm_timing": [C.c_void_p, C.c_int],
     "tnr_gemm_timing_read": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _c_i64p],
     "tnr_malloc": [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)],
@@ -55,6 +56,8 @@ _SIGNATURES = {
                         C.POINTER(C.c_double)],
     "tnr_scale": [C.c_void_p, _c_dp, C.c_int64, C.c_double],
     "tnr_diag_scale": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.c_int64, _c_dp, C.c_int, C.c_int,
+                       C.c_double],
+    "tnr_axis_scale": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.c_int64, _c_dp, C.c_int,
                        C.c_double],
     "tnr_vec_map": [C.c_void_p, _c_dp, _c_dp, C.c_int64, C.c_int, C.c_double],
     "tnr_topk_select": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.POINTER(C.c_int32),
@@ -147,8 +150,11 @@ class Context:
         self.call("tnr_get_counters", C.byref(a), C.byref(b), C.byref(f), C.byref(pb))
         t = C.c_uint64()
         self.call("tnr_get_tma_launches", C.byref(t))
+        g = C.c_double()
+        self.call("tnr_get_counter", b"grouped_gemm_launches", C.byref(g))
         return {"launches": a.value, "gemm_launches": b.value, "gemm_flops": f.value,
-                "permute_bytes": pb.value, "tma_gemm_launches": t.value}
+                "permute_bytes": pb.value, "tma_gemm_launches": t.value,
+                "grouped_gemm_launches": int(g.value)}
 
     def set_option(self, key: str, value: int):
         self.call("tnr_set_option", key.encode(), int(value))

@@ -534,3 +534,27 @@ int tnr_topk_select(tnr_context* ctx, const double* vals, int64_t n, int64_t k, 
 }
 
 }  // extern "C"
+
+extern "C" int tnr_axis_scale(tnr_context* ctx, double* A, int64_t m1, int64_t n, int64_t m2,
+                              const double* s, int mode, double p) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(mode >= 0 && mode <= 2 && m1 >= 1 && n >= 1 && m2 >= 1, "axis_scale: bad args");
+        axis_scale(&ctx->c, A, m1, n, m2, s, mode, p);
+    });
+}
+
+extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value) {
+    if (!ctx || !name || !value) return 1;
+    return guard(ctx, [&] {
+        const Counters& c = ctx->c.ctr;
+        std::string n(name);
+        if (n == "launches") *value = (double)c.launches;
+        else if (n == "gemm_launches") *value = (double)c.gemm_launches;
+        else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
+        else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "gemm_flops") *value = c.gemm_flops;
+        else if (n == "permute_bytes") *value = c.permute_bytes;
+        else throw Error(1, "unknown counter: " + n);
+    });
+}

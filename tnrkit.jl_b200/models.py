@@ -13,6 +13,28 @@ import math
 import numpy as np
 
 
+class ChargedArray(np.ndarray):
+    """Host tensor in the charge basis of a Z_N symmetry: `charges[leg][i]` is the irrep label
+    of index i of that leg, `signs[leg]` = +1 (codomain) / -1 (domain), and entries are nonzero
+    only where sum_leg sign*charge = 0 mod N -- the information a TensorKit
+    `TensorMap{Float64, Vect[ZNIrrep{N}]}` carries in its spaces."""
+
+    @classmethod
+    def wrap(cls, arr, N, charges, signs):
+        obj = np.asarray(arr, dtype=np.float64).view(cls)
+        obj.N = int(N)
+        obj.charges = [tuple(c) for c in charges]
+        obj.signs = tuple(int(s) for s in signs)
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.N = getattr(obj, "N", None)
+        self.charges = getattr(obj, "charges", None)
+        self.signs = getattr(obj, "signs", None)
+
+
 class Trivial:
     """No symmetry (TensorKit.Trivial)."""
 
@@ -79,7 +101,7 @@ def classical_ising(*args, h=0.0):
             for r, (i, j) in enumerate(pairs):
                 for c, (k, l) in enumerate(pairs):
                     t[i, j, k, l] = blk[r][c]
-        return t
+        return ChargedArray.wrap(t, 2, [(0, 1)] * 4, (1, 1, -1, -1))
     raise TypeError(f"classical_ising: unsupported symmetry {sym}")
 
 
@@ -100,7 +122,8 @@ def classical_ising_3D(*args, J=1.0):
         x, y = math.cosh(K), math.sinh(K)
         W = np.array([[math.sqrt(x), math.sqrt(y)], [math.sqrt(x), -math.sqrt(y)]])
         t = np.einsum("ai,aj,ak,al,am,an->ijklmn", W, W, W, W, W, W)
-        return np.ascontiguousarray(np.transpose(t, (0, 3, 4, 5, 1, 2)))
+        t = np.ascontiguousarray(np.transpose(t, (0, 3, 4, 5, 1, 2)))
+        return ChargedArray.wrap(t, 2, [(0, 1)] * 6, (1, 1, -1, -1, -1, -1))
     raise TypeError(f"classical_ising_3D: unsupported symmetry {sym}")
 
 
@@ -134,5 +157,6 @@ def classical_potts(*args):
         Pcm = np.kron(Wm, Wm)
         U = Pcm.conj().T @ Am @ Pcm
         Ud = U.reshape((q, q, q, q), order="F")
-        return np.ascontiguousarray(Ud.real)
+        return ChargedArray.wrap(np.ascontiguousarray(Ud.real), q, [tuple(range(q))] * 4,
+                                 (1, 1, -1, -1))
     raise TypeError(f"classical_potts: unsupported symmetry {sym}")

@@ -80,10 +80,67 @@ class TNRScheme:
         return f"{type(self).__name__}(T: {self.T.dims})"
 
 
-class TRG(TNRScheme):
+
+
+def _as_symmetric(T, ctx=None):
+    """ChargedArray (host, charge basis) -> block-sparse SymTensor on the device."""
+    from .symmetric import Leg, SymTensor
+
+    legs = []
+    for ch, sg in zip(T.charges, T.signs):
+        if list(ch) != sorted(ch):
+            raise ValueError("ChargedArray legs must be ordered by charge")
+        sect = {}
+        for q in ch:
+            sect[q] = sect.get(q, 0) + 1
+        legs.append(Leg(sect, sg))
+    return SymTensor.from_dense(np.asarray(T), T.N, legs, ctx)
+
+
+class _SymmetricMixin:
+    """TRG / BTRG accept Z_N-symmetric tensors (`classical_ising(Z2Irrep, ...)`,
+    `classical_potts(ZNIrrep[q], ...)`) and then run block-sparse: per-sector SVD with
+    sector-global truncrank, grouped per-sector GEMM.  `symmetric=False` forces the dense path."""
+
+    def _init_sym(self, T, symmetric, ctx):
+        from .symmetric import SymTensor
+
+        if isinstance(T, SymTensor):
+            self.T, self.ctx, self.sym = T, T.ctx, True
+            return True
+        if symmetric is not False and getattr(T, "charges", None) is not None:
+            self.T = _as_symmetric(T, ctx)
+            self.ctx, self.sym = self.T.ctx, True
+            return True
+        self.sym = False
+        return False
+
+
+class TRG(_SymmetricMixin, TNRScheme):
     """Tensor Renormalization Group (trg.jl)."""
     kind = _lib.TNR_TRG
     _step_fn = "tnr_trg_step"
+
+    def __init__(self, T, ctx=None, symmetric=None):
+        if not self._init_sym(T, symmetric, ctx):
+            TNRScheme.__init__(self, T, ctx)
+
+    def step(self, trunc):
+        if not self.sym:
+            return TNRScheme.step(self, trunc)
+        from .symmetric import trg_step_sym
+
+        self.T = trg_step_sym(self.T, _chi(trunc))
+        return self
+
+    def finalize(self):
+        if not self.sym:
+            return TNRScheme.finalize(self)
+        from .symmetric import sym_trace_2d
+
+        n = abs(sym_trace_2d(self.T))
+        self.T.scale(1.0 / n)
+        return n
 
 
 class HOTRG(TNRScheme):
@@ -105,12 +162,19 @@ class ATRG_3D(TNRScheme):
     _step_fn = "tnr_atrg3d_step"
 
 
-class BTRG(TNRScheme):
+class BTRG(_SymmetricMixin, TNRScheme):
     """Bond-weighted TRG (btrg.jl): fields T, S1 (vertical bonds), S2 (horizontal), k."""
     kind = _lib.TNR_BTRG
 
-    def __init__(self, T, k=-0.5, ctx=None):
-        super().__init__(T, ctx)
+    def __init__(self, T, k=-0.5, ctx=None, symmetric=None):
+        self.k = float(k)
+        if self._init_sym(T, symmetric, ctx):
+            from .symmetric import identity_weights
+
+            self.S1 = identity_weights(self.T.legs[1], self.ctx)
+            self.S2 = identity_weights(self.T.legs[0], self.ctx)
+            return
+        TNRScheme.__init__(self, T, ctx)
         # S1 = id(space(T,2)), S2 = id(space(T,1)); stored as diagonals
         self.S1 = DeviceTensor.from_numpy(np.ones(self.T.dims[1]), 1, self.ctx)
         self.S2 = DeviceTensor.from_numpy(np.ones(self.T.dims[0]), 1, self.ctx)
@@ -118,6 +182,11 @@ class BTRG(TNRScheme):
 
     def step(self, trunc):
         chi = _chi(trunc)
+        if self.sym:
+            from .symmetric import btrg_step_sym
+
+            self.T, self.S1, self.S2 = btrg_step_sym(self.T, self.S1, self.S2, self.k, chi)
+            return self
         od = self._out_dims(chi)
         out = DeviceTensor.empty(od, 2, self.ctx)
         s1 = DeviceTensor.empty((od[1],), 1, self.ctx)
@@ -130,6 +199,12 @@ class BTRG(TNRScheme):
         return self
 
     def finalize(self):
+        if self.sym:
+            from .symmetric import sym_trace_2d
+
+            n = abs(sym_trace_2d(self.T, self.S2, self.S1))
+            self.T.scale(1.0 / n)
+            return n
         n = C.c_double()
         self.ctx.call("tnr_finalize_btrg", self.T.ptr, _lib.i64(self.T.dims), self.S1.ptr,
                       self.S2.ptr, C.byref(n))

@@ -1,0 +1,383 @@
+"""Block-sparse tensors with an abelian Z_N symmetry (TensorKit `Z2Irrep`, `ZNIrrep{N}`).
+
+The host keeps the sector / block structure (which charge tuples are allowed, block shapes,
+offsets); the data of every block lives in device memory.  This mirrors how TensorKit stores
+an abelian `TensorMap`: for every coupled sector c one dense matrix whose rows / columns are
+the fusion-tree (= charge tuple) blocks of the codomain / domain.  The three operations the
+TRG / BTRG `step!` bodies need are
+
+  * contraction  = re-block both operands into coupled-sector matrices (strided block copies)
+                   and multiply ALL sectors in ONE grouped DMMA launch (`tnr_gemm_grouped`);
+  * svd_trunc    = SVD of every coupled-sector matrix + sector-GLOBAL truncrank on the device
+                   (`tnr_topk_select` over the concatenated spectra);
+  * permute      = per-block index permutation (`tnr_permute`).
+
+Conservation law: a block with charges (q_1..q_r) is present iff sum_i sign_i * q_i = 0 mod N,
+sign = +1 for codomain-like legs and -1 for domain-like legs.  All fusion / braiding symbols of
+Z_N are 1, so no recoupling coefficients appear.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+
+import numpy as np
+
+from . import _lib
+from .tensor import DeviceTensor, svd_trunc
+
+
+class Leg:
+    """Graded leg: sectors sorted by charge, `dims[q]` states of charge q, arrow `sign`."""
+
+    def __init__(self, sectors, sign):
+        items = sorted((int(q), int(d)) for q, d in dict(sectors).items() if int(d) > 0)
+        self.charges = tuple(q for q, _ in items)
+        self.dims = {q: d for q, d in items}
+        self.sign = int(sign)
+        off, acc = {}, 0
+        for q, d in items:
+            off[q] = acc
+            acc += d
+        self.offsets = off
+        self.total = acc
+
+    def flipped(self):
+        return Leg(self.dims, -self.sign)
+
+    def same_space(self, other):
+        return self.dims == other.dims
+
+    def __repr__(self):
+        return f"Leg({self.dims}, sign={self.sign:+d})"
+
+
+def _colmajor_strides(dims):
+    st, acc = [], 1
+    for d in dims:
+        st.append(acc)
+        acc *= d
+    return st
+
+
+class SymTensor:
+    """Z_N block-sparse tensor: `blocks[(q_1..q_r)]` is a dense DeviceTensor."""
+
+    def __init__(self, N, legs, blocks, ctx=None):
+        self.N = int(N)
+        self.legs = list(legs)
+        self.blocks = dict(blocks)
+        self.ctx = ctx or _lib.default_context()
+
+    # ---- structure ---------------------------------------------------------
+    def allowed(self, key):
+        return sum(l.sign * q for l, q in zip(self.legs, key)) % self.N == 0
+
+    def keys(self):
+        for key in itertools.product(*[l.charges for l in reversed(self.legs)]):
+            key = tuple(reversed(key))  # first leg fastest
+            if self.allowed(key):
+                yield key
+
+    def block_dims(self, key):
+        return tuple(l.dims[q] for l, q in zip(self.legs, key))
+
+    @property
+    def dims(self):
+        return tuple(l.total for l in self.legs)
+
+    def nnz(self):
+        return sum(math.prod(self.block_dims(k)) for k in self.blocks)
+
+    # ---- host <-> device -----------------------------------------------------
+    @classmethod
+    def from_dense(cls, arr, N, legs, ctx=None, tol=1e-12):
+        """Uploads the symmetry-allowed blocks of a dense array given in the charge basis
+        (every leg's index range ordered by sector as in `Leg.offsets`)."""
+        arr = np.asarray(arr, dtype=np.float64)
+        t = cls(N, legs, {}, ctx)
+        assert arr.shape == t.dims, (arr.shape, t.dims)
+        mask = np.zeros(arr.shape, dtype=bool)
+        for key in t.keys():
+            sl = tuple(slice(l.offsets[q], l.offsets[q] + l.dims[q]) for l, q in zip(legs, key))
+            t.blocks[key] = DeviceTensor.from_numpy(arr[sl], None, t.ctx)
+            mask[sl] = True
+        viol = np.abs(arr[~mask]).max() if (~mask).any() else 0.0
+        if viol > tol * max(1.0, np.abs(arr).max()):
+            raise ValueError(f"tensor is not Z{N} symmetric (forbidden entries up to {viol:.2e})")
+        return t
+
+    def to_dense(self):
+        out = np.zeros(self.dims)
+        for key, blk in self.blocks.items():
+            sl = tuple(slice(l.offsets[q], l.offsets[q] + l.dims[q])
+                       for l, q in zip(self.legs, key))
+            out[sl] = blk.to_numpy()
+        return out
+
+    # ---- permute -------------------------------------------------------------
+    def permute(self, perm):
+        legs = [self.legs[p] for p in perm]
+        blocks = {tuple(k[p] for p in perm): b.permute(perm) for k, b in self.blocks.items()}
+        return SymTensor(self.N, legs, blocks, self.ctx)
+
+    # ---- coupled-sector matrices ----------------------------------------------
+    def _tuples(self, which, negate):
+        """{c: [(tuple, offset, size)]} for the legs `which`; c = (+/-) sum sign*q mod N."""
+        out = {}
+        legs = [self.legs[i] for i in which]
+        for key in itertools.product(*[l.charges for l in reversed(legs)]):
+            key = tuple(reversed(key))
+            c = sum(l.sign * q for l, q in zip(legs, key)) % self.N
+            if negate:
+                c = (-c) % self.N
+            lst = out.setdefault(c, [])
+            off = lst[-1][1] + lst[-1][2] if lst else 0
+            lst.append((key, off, math.prod(l.dims[q] for l, q in zip(legs, key))))
+        return out
+
+    def matricize(self, rows, cols):
+        """Coupled-sector matrices M_c (rows_c x cols_c) for the bipartition rows | cols.
+        Returns (mats, row_tuples, col_tuples)."""
+        import torch
+
+        rt, ct = self._tuples(rows, False), self._tuples(cols, True)
+        mats = {}
+        for c in rt:
+            if c not in ct:
+                continue
+            nr = rt[c][-1][1] + rt[c][-1][2]
+            nc = ct[c][-1][1] + ct[c][-1][2]
+            buf = torch.zeros(nr * nc, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+            mats[c] = DeviceTensor(buf, (nr, nc), 1, self.ctx)
+        rlook = {c: {k: (o, s) for k, o, s in v} for c, v in rt.items()}
+        clook = {c: {k: (o, s) for k, o, s in v} for c, v in ct.items()}
+        for key, blk in self.blocks.items():
+            rk = tuple(key[i] for i in rows)
+            ck = tuple(key[i] for i in cols)
+            c = sum(self.legs[i].sign * key[i] for i in rows) % self.N
+            M = mats[c]
+            roff, _ = rlook[c][rk]
+            coff, _ = clook[c][ck]
+            self._copy_block(blk, key, rows, cols, M, roff, coff, to_matrix=True)
+        return mats, rt, ct
+
+    def _copy_block(self, blk, key, rows, cols, M, roff, coff, to_matrix):
+        """Strided copy between a tuple block (compact, leg order of self) and its slot in M."""
+        bd = self.block_dims(key)
+        sst = _colmajor_strides(bd)
+        nr = M.dims[0]
+        dst = [0] * len(bd)
+        for pos, st in zip(rows, _colmajor_strides([bd[i] for i in rows])):
+            dst[pos] = st
+        for pos, st in zip(cols, _colmajor_strides([bd[i] for i in cols])):
+            dst[pos] = st * nr
+        mptr = C.c_void_p(M.buf.data_ptr() + 8 * (roff + coff * nr))
+        if to_matrix:
+            self.ctx.call("tnr_strided_copy", blk.ptr, mptr, len(bd), _lib.i64(bd), _lib.i64(sst),
+                          _lib.i64(dst))
+        else:
+            self.ctx.call("tnr_strided_copy", mptr, blk.ptr, len(bd), _lib.i64(bd), _lib.i64(dst),
+                          _lib.i64(sst))
+
+    # ---- scaling by diagonal (per-sector) weights -------------------------------
+    def scale_leg(self, axis, weights, mode=0, p=0.0):
+        """T[..., i_axis, ...] *= f(w_{q_axis}[i_axis]) in place; weights: {charge: DeviceTensor}."""
+        for key, blk in self.blocks.items():
+            bd = self.block_dims(key)
+            m1 = math.prod(bd[:axis])
+            m2 = math.prod(bd[axis + 1:])
+            self.ctx.call("tnr_axis_scale", blk.ptr, m1, bd[axis], m2, weights[key[axis]].ptr,
+                          mode, float(p))
+        return self
+
+    def scale(self, alpha):
+        for blk in self.blocks.values():
+            self.ctx.call("tnr_scale", blk.ptr, blk.size, float(alpha))
+        return self
+
+    def __repr__(self):
+        return f"SymTensor(Z{self.N}, dims={self.dims}, blocks={len(self.blocks)})"
+
+
+# ------------------------------------------------------------------------------------
+def sym_contract(A: SymTensor, la: str, B: SymTensor, lb: str, lc: str) -> SymTensor:
+    """One binary `@tensor` contraction of block-sparse tensors: all coupled sectors are
+    multiplied in ONE grouped DMMA launch."""
+    assert A.N == B.N
+    K = [c for c in la if c in lb and c not in lc]
+    fa = [c for c in la if c not in K]
+    fb = [c for c in lb if c not in K]
+    assert sorted(fa + fb) == sorted(lc), "batch / outer labels are not supported"
+    for c in K:
+        x, y = A.legs[la.index(c)], B.legs[lb.index(c)]
+        assert x.sign == -y.sign, f"contracted leg '{c}' must have opposite arrows"
+        assert x.same_space(y), f"contracted leg '{c}': sector structure differs"
+    rows_a, cols_a = [la.index(c) for c in fa], [la.index(c) for c in K]
+    rows_b, cols_b = [lb.index(c) for c in K], [lb.index(c) for c in fb]
+    Am, art, _ = A.matricize(rows_a, cols_a)
+    Bm, _, bct = B.matricize(rows_b, cols_b)
+    import torch
+
+    ctx = A.ctx
+    Cm, probs = {}, []
+    for c in Am:
+        if c not in Bm:
+            continue
+        m, k = Am[c].dims
+        k2, n = Bm[c].dims
+        assert k == k2
+        buf = torch.empty(m * n, dtype=torch.float64, device=f"cuda:{ctx.device}")
+        Cm[c] = DeviceTensor(buf, (m, n), 1, ctx)
+        probs.append(_lib.GemmProblem(m, n, k, Am[c].buf.data_ptr(), m, Bm[c].buf.data_ptr(), k,
+                                      buf.data_ptr(), m))
+    if probs:
+        arr = (_lib.GemmProblem * len(probs))(*probs)
+        ctx.call("tnr_gemm_grouped", b"N", b"N", len(probs), arr, 1.0, 0.0)
+    # split the sector matrices into tuple blocks, directly in the requested leg order
+    out_legs_nat = [A.legs[i] for i in rows_a] + [B.legs[i] for i in cols_b]
+    nat = fa + fb
+    order = [nat.index(c) for c in lc]
+    out = SymTensor(A.N, [out_legs_nat[i] for i in order], {}, ctx)
+    for c, M in Cm.items():
+        nr = M.dims[0]
+        for (ka, roff, _), (kb, coff, _) in itertools.product(art[c], bct[c]):
+            key_nat = ka + kb
+            bd_nat = tuple(l.dims[q] for l, q in zip(out_legs_nat, key_nat))
+            src = _colmajor_strides(bd_nat[:len(ka)]) + \
+                [s * nr for s in _colmajor_strides(bd_nat[len(ka):])]
+            key = tuple(key_nat[i] for i in order)
+            bd = tuple(bd_nat[i] for i in order)
+            blk = DeviceTensor.empty(bd, None, ctx)
+            mptr = C.c_void_p(M.buf.data_ptr() + 8 * (roff + coff * nr))
+            ctx.call("tnr_strided_copy", mptr, blk.ptr, len(bd), _lib.i64(bd),
+                     _lib.i64([src[i] for i in order]), _lib.i64(_colmajor_strides(bd)))
+            out.blocks[key] = blk
+    return out
+
+
+def sym_svd_trunc(T: SymTensor, ncod: int, chi: int):
+    """svd_trunc(T; trunc = truncrank(chi)) for a block-sparse tensor: per-sector SVD and a
+    sector-global choice of the chi largest singular values (on the device).
+    Returns U [cod..., bond(-)], S {c: DeviceTensor}, Vt [bond(+), dom...], eps."""
+    import torch
+
+    ctx = T.ctx
+    r = len(T.legs)
+    rows, cols = list(range(ncod)), list(range(ncod, r))
+    mats, rt, ct = T.matricize(rows, cols)
+    fac, order = {}, sorted(mats)
+    eps2 = 0.0
+    for c in order:
+        U, S, Vt, e = svd_trunc(mats[c], 1, chi)
+        fac[c] = (U, S, Vt)
+        eps2 += e * e
+    allS = torch.cat([fac[c][1].buf[: fac[c][1].size] for c in order])
+    n = allS.numel()
+    ranks = (C.c_int32 * n)()
+    e_sel = C.c_double()
+    ctx.call("tnr_topk_select", C.c_void_p(allS.data_ptr()), n, chi, ranks, C.byref(e_sel))
+    eps = math.sqrt(eps2 + e_sel.value ** 2)
+    keep, pos = {}, 0
+    for c in order:
+        ns = fac[c][1].size
+        keep[c] = sum(1 for j in range(pos, pos + ns) if ranks[j] < chi)
+        pos += ns
+    bond = {c: k for c, k in keep.items() if k > 0}
+    Ut = SymTensor(T.N, [T.legs[i] for i in rows] + [Leg(bond, -1)], {}, ctx)
+    Vt_ = SymTensor(T.N, [Leg(bond, +1)] + [T.legs[i] for i in cols], {}, ctx)
+    Sd = {}
+    for c, k in bond.items():
+        U, S, Vt = fac[c]
+        Sd[c] = DeviceTensor(S.buf[:k].clone(), (k,), 1, ctx)
+        nr, nc = mats[c].dims
+        kc = S.size  # leading dimension of Vt_c
+        for key, roff, size in rt[c]:
+            bd = tuple(T.legs[i].dims[q] for i, q in zip(rows, key)) + (k,)
+            blk = DeviceTensor.empty(bd, None, ctx)
+            src = C.c_void_p(U.buf.data_ptr() + 8 * roff)
+            ctx.call("tnr_strided_copy", src, blk.ptr, 2, _lib.i64((size, k)), _lib.i64((1, nr)),
+                     _lib.i64((1, size)))
+            Ut.blocks[key + (c,)] = blk
+        for key, coff, size in ct[c]:
+            bd = (k,) + tuple(T.legs[i].dims[q] for i, q in zip(cols, key))
+            blk = DeviceTensor.empty(bd, None, ctx)
+            src = C.c_void_p(Vt.buf.data_ptr() + 8 * coff * kc)
+            ctx.call("tnr_strided_copy", src, blk.ptr, 2, _lib.i64((k, size)), _lib.i64((1, kc)),
+                     _lib.i64((1, k)))
+            Vt_.blocks[(c,) + key] = blk
+    return Ut, Sd, Vt_, eps
+
+
+def vec_map(S, mode, p=0.0):
+    """{c: f(S_c)}: sqrt (mode 1) / pseudopow(., p) (mode 2) of per-sector weight vectors."""
+    out = {}
+    for c, s in S.items():
+        o = DeviceTensor.empty(s.dims, 1, s.ctx)
+        s.ctx.call("tnr_vec_map", s.ptr, o.ptr, s.size, mode, float(p))
+        out[c] = o
+    return out
+
+
+def sym_trace_2d(T: SymTensor, w_leg0=None, w_leg1=None):
+    """sum T[1 2; 2 1] (optionally weighted: BTRG's  T[1 2;4 3] S1[4;2] S2[3;1])."""
+    total = 0.0
+    for key, blk in T.blocks.items():
+        q1, q2, q3, q4 = key
+        if q3 != q2 or q4 != q1:
+            continue
+        d = T.block_dims(key)
+        assert d[0] == d[3] and d[1] == d[2]
+        st = _colmajor_strides(d)
+        dims = (d[0], d[1])
+        strides = (st[0] + st[3], st[1] + st[2])
+        w = (C.c_void_p * 2)(w_leg0[q1].buf.data_ptr() if w_leg0 else None,
+                             w_leg1[q2].buf.data_ptr() if w_leg1 else None)
+        s = C.c_double()
+        T.ctx.call("tnr_strided_sum", blk.ptr, 2, _lib.i64(dims), _lib.i64(strides),
+                   w if (w_leg0 or w_leg1) else None, C.byref(s))
+        total += s.value
+    return total
+
+
+# ------------------------------------------------------------------------------------
+# step! / finalize! bodies on block-sparse tensors (configs[2]: TRG / BTRG on Z2 / ZN)
+# ------------------------------------------------------------------------------------
+def trg_step_sym(T: SymTensor, chi: int) -> SymTensor:
+    """step!(::TRG) on a Z_N tensor -- src/schemes/trg.jl:38-44 with per-sector SVD12."""
+    U, S, V, _ = sym_svd_trunc(T, 2, chi)
+    rs = vec_map(S, 1)
+    A = U.scale_leg(2, rs)            # U * sqrt(s)      [a b k]
+    B = V.scale_leg(0, rs)            # sqrt(s) * V      [k c d]
+    U2, S2, V2, _ = sym_svd_trunc(T.permute((1, 3, 0, 2)), 2, chi)
+    rs2 = vec_map(S2, 1)
+    Cc = U2.scale_leg(2, rs2)
+    D = V2.scale_leg(0, rs2)
+    # T[-1 -2;-3 -4] := D[-2;1 2] * B[-1;4 1] * C[4 3;-3] * A[3 2;-4]
+    X = sym_contract(D, "bpq", B, "asp", "bqas")
+    Y = sym_contract(Cc, "src", A, "rqd", "scqd")
+    return sym_contract(X, "bqas", Y, "scqd", "abcd")
+
+
+def btrg_step_sym(T: SymTensor, S1, S2, k: float, chi: int):
+    """step!(::BTRG) on a Z_N tensor -- src/schemes/btrg.jl:62-97.  S1, S2: {charge: diag}."""
+    pa = (1.0 - k) / 2.0
+    U, S, V, _ = sym_svd_trunc(T, 2, chi)
+    Sa, S1n = vec_map(S, 2, pa), vec_map(S, 2, k)
+    A = U.scale_leg(2, Sa)            # [p s c]  (btrg labels A[6 5;-3])
+    B = V.scale_leg(0, Sa)            # [b q r]
+    U2, Sv, V2, _ = sym_svd_trunc(T.permute((2, 0, 3, 1)), 2, chi)
+    Sa2, S2n = vec_map(Sv, 2, pa), vec_map(Sv, 2, k)
+    Cc = U2.scale_leg(2, Sa2)         # [s r d]
+    D = V2.scale_leg(0, Sa2)          # [a p q]
+    # T := D[-1;4 7] S1[1;7] B[-2;1 3] S2[3;2] C[8 2;-4] S1[8;5] A[6 5;-3] S2[4;6]
+    B.scale_leg(1, S1).scale_leg(2, S2)   # B'[b,q,r] = B s1[q] s2[r]
+    A.scale_leg(0, S2).scale_leg(1, S1)   # A'[p,s,c] = A s2[p] s1[s]
+    X = sym_contract(D, "apq", B, "bqr", "apbr")
+    Y = sym_contract(Cc, "srd", A, "psc", "rdpc")
+    return sym_contract(X, "apbr", Y, "rdpc", "abcd"), S1n, S2n
+
+
+def identity_weights(leg: Leg, ctx):
+    return {q: DeviceTensor.from_numpy(np.ones(d), 1, ctx) for q, d in leg.dims.items()}
