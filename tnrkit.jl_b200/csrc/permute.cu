@@ -6,9 +6,10 @@
 //
 // A permutation is a strided copy dst[i.dstride] = src[i.sstride].  After merging
 // index groups that stay adjacent, either the fastest index is the same on both
-// sides (vectorisable row copy) or it differs, in which case a 32x32 tile over
-// (src-fastest, dst-fastest) is transposed through padded shared memory so both
-// the global reads and the global writes are coalesced.
+// sides (row copy) or it differs, in which case a tile over (src-fastest, dst-fastest)
+// -- whole legs when the bond dimension is <= 48, 32 x 32 otherwise -- times a batch of
+// slices of the next index is transposed through padded shared memory, so that global reads
+// run along the source's contiguous leg and global writes along the destination's.
 #include <algorithm>
 
 #include "common.cuh"
@@ -28,22 +29,25 @@ struct CopyParams {
     long long nj, sj_s, sj_d;  // dst-fastest dim
     long long tiles_i, tiles_j;
     int ti, tj;                // tile extents along i and j
+    // slice batch: nb consecutive values of a third index per block
+    long long nbdim, sb_s, sb_d, tiles_b;
+    int nb;
     long long total;           // total elements (row kernel)
 };
 
-// Tile extents adapt to short legs: a leg of extent <= 48 (bond dimension chi = 24, 32, 48)
-// is taken whole, so every lane moves data and every 32-byte sector is fully used.
 constexpr int TMAX = 48;
 
 __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restrict__ src,
                                                          double* __restrict__ dst,
                                                          const CopyParams p) {
-    __shared__ double tile[TMAX * (TMAX + 1)];
+    extern __shared__ double tile[];  // [nb][TJ][TI + 1]
     long long bid = blockIdx.x;
     long long ti = bid % p.tiles_i;
     bid /= p.tiles_i;
     long long tj = bid % p.tiles_j;
     bid /= p.tiles_j;
+    long long tb = bid % p.tiles_b;
+    bid /= p.tiles_b;
     long long soff = 0, doff = 0;
 #pragma unroll
     for (int d = 0; d < MAXR; ++d) {
@@ -55,21 +59,31 @@ __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restric
         }
     }
     const int TI = p.ti, TJ = p.tj;
-    const long long i0 = ti * TI, j0 = tj * TJ;
+    const long long i0 = ti * TI, j0 = tj * TJ, b0 = tb * p.nb;
     const int ni = (int)min((long long)TI, p.ni - i0), nj = (int)min((long long)TJ, p.nj - j0);
-    const int count = ni * nj;
-    const double* sp = src + soff + i0 * p.si_s + j0 * p.sj_s;
-    double* dp = dst + doff + i0 * p.si_d + j0 * p.sj_d;
-    // read: i fastest (src contiguous)
-    for (int idx = threadIdx.x; idx < count; idx += 256) {
-        int i = idx % ni, j = idx / ni;
-        tile[j * (TMAX + 1) + i] = sp[i * p.si_s + j * p.sj_s];
+    const int nb = (int)min((long long)p.nb, p.nbdim - b0);
+    const double* sp = src + soff + i0 * p.si_s + j0 * p.sj_s + b0 * p.sb_s;
+    double* dp = dst + doff + i0 * p.si_d + j0 * p.sj_d + b0 * p.sb_d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = TI + 1, slab = TJ * pitch;
+    // read: one warp per (j, b) row, lanes along i (source contiguous)
+    const int rrows = nj * nb;
+#pragma unroll 4
+    for (int row = warp; row < rrows; row += 8) {
+        int j = row % nj, b = row / nj;
+        const double* g = sp + j * p.sj_s + b * p.sb_s;
+        double* t = tile + b * slab + j * pitch;
+        for (int i = lane; i < ni; i += 32) t[i] = g[i * p.si_s];
     }
     __syncthreads();
-    // write: j fastest (dst contiguous)
-    for (int idx = threadIdx.x; idx < count; idx += 256) {
-        int j = idx % nj, i = idx / nj;
-        dp[i * p.si_d + j * p.sj_d] = tile[j * (TMAX + 1) + i];
+    // write: one warp per (i, b) row, lanes along j (destination contiguous)
+    const int wrows = ni * nb;
+#pragma unroll 4
+    for (int row = warp; row < wrows; row += 8) {
+        int i = row % ni, b = row / ni;
+        double* g = dp + i * p.si_d + b * p.sb_d;
+        const double* t = tile + b * slab + i;
+        for (int j = lane; j < nj; j += 32) g[j * p.sj_d] = t[j * pitch];
     }
 }
 
@@ -144,7 +158,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         ctx->ctr.launches++;
         return;
     }
-    TNR_CHECK((int)m.size() <= MAXR + 2, "strided_copy: too many index groups after merging");
+    TNR_CHECK((int)m.size() <= MAXR + 3, "strided_copy: too many index groups after merging");
     // dst-fastest is m[0]; find src-fastest
     size_t js = 0;
     for (size_t i = 1; i < m.size(); ++i)
@@ -162,21 +176,37 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
     } else {
         p.ni = m[js].n; p.si_s = m[js].s; p.si_d = m[js].d;
         p.nj = m[0].n; p.sj_s = m[0].s; p.sj_d = m[0].d;
+        p.ti = p.ni <= TMAX ? (int)p.ni : 32;
+        p.tj = p.nj <= TMAX ? (int)p.nj : 32;
+        // batch index: the remaining group with the smallest source stride (keeps the reads
+        // of one block inside few DRAM pages); batch size targets <= 40 KB of shared memory
+        size_t jb = (size_t)-1;
+        for (size_t i = 1; i < m.size(); ++i) {
+            if (i == js) continue;
+            if (jb == (size_t)-1 || m[i].s < m[jb].s) jb = i;
+        }
+        const long long slab_bytes = (long long)p.tj * (p.ti + 1) * 8;
+        if (jb != (size_t)-1) {
+            p.nbdim = m[jb].n; p.sb_s = m[jb].s; p.sb_d = m[jb].d;
+            p.nb = (int)std::max<long long>(1, std::min<long long>(p.nbdim, 40960 / slab_bytes));
+        } else {
+            p.nbdim = 1; p.sb_s = 0; p.sb_d = 0; p.nb = 1;
+        }
+        p.tiles_b = (p.nbdim + p.nb - 1) / p.nb;
         p.rank = 0;
         long long outer = 1;
         for (size_t i = 1; i < m.size(); ++i) {
-            if (i == js) continue;
+            if (i == js || i == jb) continue;
             p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
             p.rank++;
             outer *= m[i].n;
         }
-        p.ti = p.ni <= TMAX ? (int)p.ni : 32;
-        p.tj = p.nj <= TMAX ? (int)p.nj : 32;
         p.tiles_i = (p.ni + p.ti - 1) / p.ti;
         p.tiles_j = (p.nj + p.tj - 1) / p.tj;
-        long long blocks = p.tiles_i * p.tiles_j * outer;
+        long long blocks = p.tiles_i * p.tiles_j * p.tiles_b * outer;
         TNR_CHECK(blocks < (1LL << 31), "strided_copy: grid too large");
-        copy_tiled_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, dst, p);
+        size_t smem = (size_t)p.nb * slab_bytes;
+        copy_tiled_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
     }
     TNR_CUDA(cudaGetLastError());
     ctx->ctr.launches++;
