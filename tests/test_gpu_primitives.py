@@ -156,3 +156,42 @@ def test_gemm_tma_fallback_on_odd_leading_dimension(tk, ctx):
     got, ref = _gemm(tk, ctx, "T", "N", 1601, 1555, 77, rng)
     assert ctx.counters()["tma_gemm_launches"] == before
     assert np.abs(got - ref).max() <= 1e-11
+
+
+def _counter(ctx, name):
+    import ctypes as C
+    v = C.c_double()
+    ctx.call("tnr_get_counter", name.encode(), C.byref(v))
+    return v.value
+
+
+@pytest.mark.parametrize("n,chi,decay", [(1536, 32, 8), (2048, 64, 12), (1024, 16, 4)])
+def test_eigh_trunc_subspace_path(tk, ctx, n, chi, decay):
+    """n >= 1024 with chi << n: top-chi eigenpairs come from the GEMM-rich block subspace
+    iteration; values, truncation error and the invariant subspace must match LAPACK."""
+    rng = np.random.default_rng(n + chi)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.logspace(0, -decay, n)
+    mm = (q * lam) @ q.T
+    mm = 0.5 * (mm + mm.T)
+    before = _counter(ctx, "subspace_eigh")
+    W, V, eps = tk.eigh_trunc(tk.DeviceTensor.from_numpy(mm), chi)
+    assert _counter(ctx, "subspace_eigh") == before + 1, "subspace solver not used / fell back"
+    w, v = W.to_numpy(), V.to_numpy()
+    wr, vr = np.linalg.eigh(mm)
+    order = np.argsort(-np.abs(wr))
+    assert np.abs(w - wr[order[:chi]]).max() <= 1e-12 * np.abs(wr).max()
+    assert abs(eps - np.linalg.norm(wr[order[chi:]])) <= 1e-7 * np.abs(wr).max()
+    assert np.abs(v.T @ v - np.eye(chi)).max() <= 1e-12
+    pr = vr[:, order[:chi]]
+    # projector onto the kept subspace (gauge invariant); conditioning ~ eps / gap
+    gap = abs(wr[order[chi - 1]]) - abs(wr[order[chi]])
+    assert np.abs(v @ v.T - pr @ pr.T).max() <= 1e-13 * np.abs(wr).max() / gap * 50
+    # and the full-Jacobi path gives the same answer
+    ctx.set_option("disable_subspace", 1)
+    try:
+        W2, V2, eps2 = tk.eigh_trunc(tk.DeviceTensor.from_numpy(mm), chi)
+    finally:
+        ctx.set_option("disable_subspace", 0)
+    assert np.abs(W2.to_numpy() - w).max() <= 1e-12 * np.abs(wr).max()
+    assert abs(eps2 - eps) <= 1e-7 * np.abs(wr).max()

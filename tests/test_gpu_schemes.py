@@ -102,3 +102,19 @@ def test_golden_fixture_norms(tk):
         got = np.array(tk.run(cls(T), tk.truncrank(chi), tk.maxiter(n), verbosity=0))
         ref = np.array(g[key])
         assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL, key
+
+
+def test_hotrg_chi32_uses_subspace_eigh_and_matches_oracle(tk):
+    """HOTRG at chi = 32: the projector Gram matrices are 1024 x 1024 and only 32 eigenpairs are
+    kept, so eigh_trunc runs the block subspace iteration; norms must still match LAPACK."""
+    import ctypes as C
+
+    ctx = tk.default_context()
+    v0 = C.c_double()
+    ctx.call("tnr_get_counter", b"subspace_eigh", C.byref(v0))
+    T = tk.classical_ising(tk.Trivial, 0.43)
+    got, ref = _norms(tk, tk.HOTRG, o.HOTRG, T, 32, 4)
+    v1 = C.c_double()
+    ctx.call("tnr_get_counter", b"subspace_eigh", C.byref(v1))
+    assert v1.value > v0.value, "subspace path was never taken"
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL

@@ -137,6 +137,7 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return 1;
     return guard(ctx, [&] {
         if (std::strcmp(key, "disable_tma") == 0) ctx->c.disable_tma = value != 0;
+        else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else throw Error(1, std::string("unknown option: ") + key);
     });
 }
@@ -553,6 +554,8 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "gemm_launches") *value = (double)c.gemm_launches;
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
+        else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;
         else if (n == "gemm_flops") *value = c.gemm_flops;
         else if (n == "permute_bytes") *value = c.permute_bytes;
         else throw Error(1, "unknown counter: " + n);

@@ -35,6 +35,8 @@ struct Counters {
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
     unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
+    unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
+    unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
     double permute_bytes = 0.0;            // read+write bytes moved by permute kernels
 };
@@ -48,6 +50,7 @@ struct Context {
     // optional timing of the big GEMM (dominant kernel) with events on ctx->stream
     bool time_gemm = false;
     bool disable_tma = false;  // force the cp.async GEMM (A/B testing)
+    bool disable_subspace = false;  // force full Jacobi in eigh_trunc
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     std::string last_error;
@@ -119,6 +122,9 @@ void axis_scale(Context* ctx, double* A, long long m1, long long n, long long m2
 void symmetrize(Context* ctx, double* A, long long n);  // A = (A + A^T)/2
 void set_identity(Context* ctx, double* A, long long n);
 void fill_zero(Context* ctx, double* A, long long n);
+void fill_random(Context* ctx, double* x, long long n, unsigned long long seed);
+void axpy(Context* ctx, double* y, const double* x, double alpha, long long n);  // y += alpha x
+void sum_squares(Context* ctx, const double* x, long long n, double* dev_out);   // deterministic
 // dot of two strided "vectors" with weights: out = |sum_{i,j..}|, used by BTRG finalize
 // dst = flag ? a : b, flag = (*epsA > *epsB)  (device side choice, HOTRG projector pick)
 void select_copy(Context* ctx, double* dst, const double* a, const double* b, long long n,

@@ -3,6 +3,7 @@
 // Reference: /root/reference/src/utility/finalize.jl:4-14,56-66,
 // src/schemes/btrg.jl:51-60, src/schemes/hotrg.jl:106-118.
 #include "common.cuh"
+#include <algorithm>
 
 namespace tnr {
 namespace {
@@ -187,6 +188,86 @@ void select_copy(Context* ctx, double* dst, const double* a, const double* b, lo
     select_copy_kernel<<<nblk(n), 256, 0, ctx->stream>>>(dst, a, b, n, eps_a, eps_b, eps_out);
     TNR_CUDA(cudaGetLastError());
     ctx->ctr.launches++;
+}
+
+}  // namespace tnr
+
+// ---- helpers of the block subspace eigensolver (tensor_ops.cu: eigh_topk) ----
+namespace tnr {
+namespace {
+
+__global__ void fill_random_kernel(double* x, long long n, unsigned long long seed) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // splitmix64 hash -> uniform(-1, 1); deterministic for a given (seed, i)
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    x[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+__global__ void axpy_kernel(double* y, const double* x, double alpha, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] += alpha * x[i];
+}
+
+// two-pass deterministic sum of squares
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const double* __restrict__ x,
+                                                            long long n, double* partial) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+        double v = x[i];
+        acc += v * v;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) sum_final_kernel(const double* partial, int n, double* out) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+}  // namespace
+
+void fill_random(Context* ctx, double* x, long long n, unsigned long long seed) {
+    if (n <= 0) return;
+    fill_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, n, seed);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
+void axpy(Context* ctx, double* y, const double* x, double alpha, long long n) {
+    if (n <= 0) return;
+    axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(y, x, alpha, n);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
+void sum_squares(Context* ctx, const double* x, long long n, double* dev_out) {
+    int blocks = (int)std::min<long long>(1024, (n + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    double* partial = dalloc(ctx, blocks);
+    sumsq_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(x, n, partial);
+    sum_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, dev_out);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches += 2;
+    dfree(ctx, partial);
 }
 
 }  // namespace tnr

@@ -2,6 +2,7 @@
 // skipped whenever the operand is already a matrix in one of the layouts the DMMA
 // kernel reads natively) and the truncated factorizations built on the Jacobi engine.
 #include <algorithm>
+#include <cmath>
 
 #include "tensor.hpp"
 
@@ -197,7 +198,7 @@ Trunc svd_trunc(const DT& T, int ncod, int chi) {
     return out;
 }
 
-Trunc eigh_trunc(DT MM, int ncod, int chi) {
+static Trunc eigh_trunc_jacobi(DT MM, int ncod, int chi) {
     Context* ctx = MM.ctx;
     long long n = prod(MM.d, 0, ncod);
     TNR_CHECK(prod(MM.d, ncod) == n, "eigh_trunc: matrix must be square");
@@ -238,6 +239,146 @@ DT orth_r(const DT& T, int ncod) {
     permute(ctx, V.p, R.p, 2, dd, pp);
     diag_scale(ctx, R.p, n, n, n, vals.p, true, 0, 0.0);
     return R;
+}
+
+}  // namespace tnr
+
+// ---------------------------------------------------------------------------
+// Top-chi eigenpairs of a large symmetric matrix without a full decomposition.
+//
+// `eigh_trunc!(MM; trunc = truncrank(chi))` keeps chi of n = chi_in^2 eigenpairs (HOTRG at
+// chi = 64: 64 of 4096).  Block subspace iteration with Rayleigh-Ritz finds exactly those:
+// every iteration is one n x n x b DMMA GEMM (b = 2 chi) plus b x b work (the small dense
+// eigenproblems reuse the Jacobi engine).  The iteration is certified by the residuals
+// ||MM x - theta x|| <= 1e-13 |theta|_max of the kept pairs; if it does not certify (or the
+// kept spectrum is numerically rank deficient) the caller falls back to the full Jacobi
+// decomposition, so results never depend on the fast path being taken.
+// ---------------------------------------------------------------------------
+namespace tnr {
+namespace {
+
+void d2h(Context* ctx, double* dst, const double* src, size_t n) {
+    TNR_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TNR_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+void h2d(Context* ctx, double* dst, const double* src, size_t n) {
+    TNR_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TNR_CUDA(cudaStreamSynchronize(ctx->stream));  // src is a host stack/vector buffer
+}
+
+// Q <- orthonormal basis of span(Y) through the eigen-decomposition of the Gram matrix
+// (columns of Y are expected to be roughly equilibrated; directions below 1e-14 relative
+// weight are dropped, i.e. set to zero).
+DT gram_orthonormalize(Context* ctx, const DT& Y, long long n, long long b) {
+    DT G(ctx, {b, b});
+    gemm(ctx, 'T', 'N', (int)b, (int)b, (int)n, 1.0, Y.p, n, Y.p, n, 0.0, G.p, b);
+    Trunc e = eigh_trunc_jacobi(std::move(G), 1, (int)b);
+    std::vector<double> lam(b), sc(b);
+    d2h(ctx, lam.data(), e.S.p, b);
+    for (long long j = 0; j < b; ++j)
+        sc[j] = (lam[j] > 1e-28 * lam[0] && lam[j] > 0.0) ? 1.0 / std::sqrt(lam[j]) : 0.0;
+    DT scd(ctx, {b});
+    h2d(ctx, scd.p, sc.data(), b);
+    DT Q(ctx, {n, b});
+    gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Y.p, n, e.U.p, b, 0.0, Q.p, n);
+    diag_scale(ctx, Q.p, n, b, n, scd.p, false, 0, 0.0);
+    return Q;
+}
+
+bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out) {
+    long long b = std::min(n, std::max(2 * k, k + 64));
+    b += (b & 1);
+    DT f2(ctx, {1});
+    sum_squares(ctx, MM.p, n * n, f2.p);
+    DT Y0(ctx, {n, b});
+    fill_random(ctx, Y0.p, n * b, 0x7e57c0deULL);
+    DT Q = gram_orthonormalize(ctx, Y0, n, b);
+    Q = gram_orthonormalize(ctx, Q, n, b);
+    Y0.release();
+    std::vector<double> theta(b), rn(k), sc(b);
+    DT QS, Th;
+    double best = 1e300;
+    bool certified = false;
+    const int maxit = 120;
+    int stalled = 0;
+    for (int it = 0; it < maxit; ++it) {
+        DT Z(ctx, {n, b});
+        gemm(ctx, 'N', 'N', (int)n, (int)b, (int)n, 1.0, MM.p, n, Q.p, n, 0.0, Z.p, n);
+        DT H(ctx, {b, b});
+        gemm(ctx, 'T', 'N', (int)b, (int)b, (int)n, 1.0, Q.p, n, Z.p, n, 0.0, H.p, b);
+        Trunc e = eigh_trunc_jacobi(std::move(H), 1, (int)b);  // Ritz pairs, |theta| descending
+        DT QSn(ctx, {n, b}), ZS(ctx, {n, b});
+        gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Q.p, n, e.U.p, b, 0.0, QSn.p, n);
+        gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Z.p, n, e.U.p, b, 0.0, ZS.p, n);
+        Z.release();
+        // residuals of the kept pairs: R = MM x - theta x = ZS[:, :k] - QS[:, :k] diag(theta)
+        DT R(ctx, {n, k});
+        TNR_CUDA(cudaMemcpyAsync(R.p, QSn.p, n * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        diag_scale(ctx, R.p, n, k, n, e.S.p, false, 0, 0.0);
+        scale(ctx, R.p, n * k, -1.0);
+        axpy(ctx, R.p, ZS.p, 1.0, n * k);
+        DT rnd(ctx, {k});
+        column_values(ctx, R.p, n, k, n, nullptr, 0, rnd.p, false);
+        d2h(ctx, theta.data(), e.S.p, b);
+        d2h(ctx, rn.data(), rnd.p, k);
+        double tmax = std::fabs(theta[0]), res = 0.0;
+        for (long long j = 0; j < k; ++j) res = std::max(res, rn[j]);
+        res = (tmax > 0.0) ? res / tmax : 0.0;
+        if (!std::isfinite(res)) return false;
+        QS = std::move(QSn);
+        Th = std::move(e.S);
+        if (res <= 1e-13) { certified = true; break; }
+        // stagnation at the rounding floor still certifies when the floor is tight enough
+        if (res > 0.7 * best) ++stalled; else stalled = 0;
+        best = std::min(best, res);
+        if (stalled >= 3 && best <= 2e-12) { certified = true; break; }
+        if (stalled >= 8) return false;
+        // next basis: Ritz-rotated images, equilibrated by 1/|theta|, re-orthonormalised
+        for (long long j = 0; j < b; ++j)
+            sc[j] = (std::fabs(theta[j]) > 1e-14 * tmax) ? 1.0 / std::fabs(theta[j]) : 0.0;
+        DT scd(ctx, {b});
+        h2d(ctx, scd.p, sc.data(), b);
+        diag_scale(ctx, ZS.p, n, b, n, scd.p, false, 0, 0.0);
+        Q = gram_orthonormalize(ctx, ZS, n, b);
+    }
+    if (!certified) return false;
+    if (!(std::fabs(theta[k - 1]) > 1e-13 * std::fabs(theta[0]))) return false;  // rank deficient
+    TNR_CUDA(cudaMemcpyAsync(out.U.p, QS.p, n * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    TNR_CUDA(cudaMemcpyAsync(out.S.p, Th.p, k * sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    // eps = ||discarded eigenvalues||_2: Ritz values k..b-1 explicitly, the rest from the
+    // Frobenius norm
+    double F2 = 0.0, kept = 0.0, mid = 0.0;
+    d2h(ctx, &F2, f2.p, 1);
+    for (long long j = 0; j < b; ++j) (j < k ? kept : mid) += theta[j] * theta[j];
+    double tail = std::max(0.0, F2 - kept - mid);
+    double eps = std::sqrt(mid + tail);
+    h2d(ctx, out.eps.p, &eps, 1);
+    ctx->ctr.subspace_eigh++;
+    return true;
+}
+
+}  // namespace
+
+Trunc eigh_trunc(DT MM, int ncod, int chi) {
+    Context* ctx = MM.ctx;
+    long long n = prod(MM.d, 0, ncod);
+    TNR_CHECK(prod(MM.d, ncod) == n, "eigh_trunc: matrix must be square");
+    long long k = std::min<long long>(chi, n);
+    if (!ctx->disable_subspace && n >= 1024 && std::max(2 * k, k + 64) <= n / 4) {
+        Dims cod(MM.d.begin(), MM.d.begin() + ncod);
+        Trunc out;
+        Dims ud = cod; ud.push_back(k);
+        out.U = DT(ctx, ud);
+        out.S = DT(ctx, {k});
+        out.eps = DT(ctx, {1});
+        symmetrize(ctx, MM.p, n);  // project_hermitian!
+        if (eigh_topk(ctx, MM, n, k, out)) return out;
+        ctx->ctr.subspace_fallbacks++;
+    }
+    return eigh_trunc_jacobi(std::move(MM), ncod, chi);
 }
 
 }  // namespace tnr
