@@ -195,3 +195,29 @@ def test_eigh_trunc_subspace_path(tk, ctx, n, chi, decay):
         ctx.set_option("disable_subspace", 0)
     assert np.abs(W2.to_numpy() - w).max() <= 1e-12 * np.abs(wr).max()
     assert abs(eps2 - eps) <= 1e-7 * np.abs(wr).max()
+
+
+@pytest.mark.parametrize("m,n,chi,decay", [(1536, 1536, 32, 8), (2048, 1100, 48, 10), (1100, 2300, 16, 5)])
+def test_svd_trunc_subspace_path(tk, ctx, m, n, chi, decay):
+    """min(m, n) >= 1024 with chi << min(m, n): the top-chi triplets come from the block subspace
+    iteration (GEMM + thin Jacobi); spectrum, truncation error and the rank-chi approximation
+    must match LAPACK, and the full-Jacobi path must agree."""
+    rng = np.random.default_rng(m + n + chi)
+    r = min(m, n)
+    u0, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    v0, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    s0 = np.logspace(0, -decay, r)
+    a = (u0 * s0) @ v0.T
+    before = _counter(ctx, "subspace_svd")
+    U, S, Vt, eps = tk.svd_trunc(tk.DeviceTensor.from_numpy(a), 1, chi)
+    assert _counter(ctx, "subspace_svd") == before + 1, "subspace solver not used / fell back"
+    u, s, vt = U.to_numpy(), S.to_numpy(), Vt.to_numpy()
+    sref = np.linalg.svd(a, compute_uv=False)
+    assert np.abs(s - sref[:chi]).max() <= 1e-12 * sref[0]
+    assert abs(eps - np.linalg.norm(sref[chi:])) <= 1e-7 * sref[0]
+    assert np.abs(u.T @ u - np.eye(chi)).max() <= 1e-12
+    assert np.abs(vt @ vt.T - np.eye(chi)).max() <= 1e-12
+    uu, ss, vv = np.linalg.svd(a, full_matrices=False)
+    best = (uu[:, :chi] * ss[:chi]) @ vv[:chi]
+    gap = sref[chi - 1] - sref[chi]
+    assert np.abs((u * s) @ vt - best).max() <= 1e-13 * sref[0] ** 2 / gap * 50

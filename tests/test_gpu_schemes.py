@@ -118,3 +118,17 @@ def test_hotrg_chi32_uses_subspace_eigh_and_matches_oracle(tk):
     ctx.call("tnr_get_counter", b"subspace_eigh", C.byref(v1))
     assert v1.value > v0.value, "subspace path was never taken"
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+
+
+def test_trg_chi32_uses_subspace_svd_and_matches_oracle(tk):
+    """TRG at chi = 32 on the dense path: 1024 x 1024 matrices, 32 triplets kept -> subspace SVD."""
+    import ctypes as C
+
+    ctx = tk.default_context()
+    v0, v1 = C.c_double(), C.c_double()
+    ctx.call("tnr_get_counter", b"subspace_svd", C.byref(v0))
+    T = tk.classical_ising(tk.Trivial, 0.43)
+    got, ref = _norms(tk, tk.TRG, o.TRG, T, 32, 8)
+    ctx.call("tnr_get_counter", b"subspace_svd", C.byref(v1))
+    assert v1.value > v0.value, "subspace SVD path was never taken"
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL

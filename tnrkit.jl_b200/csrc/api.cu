@@ -555,6 +555,7 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
+        else if (n == "subspace_svd") *value = (double)c.subspace_svd;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;
         else if (n == "gemm_flops") *value = c.gemm_flops;
         else if (n == "permute_bytes") *value = c.permute_bytes;

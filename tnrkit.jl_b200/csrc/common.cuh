@@ -36,6 +36,7 @@ struct Counters {
     unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
+    unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
     double permute_bytes = 0.0;            // read+write bytes moved by permute kernels

@@ -155,7 +155,7 @@ DT transpose2d(const DT& a, long long m, long long n) {  // a is m x n -> n x m
 
 }  // namespace
 
-Trunc svd_trunc(const DT& T, int ncod, int chi) {
+static Trunc svd_trunc_jacobi(const DT& T, int ncod, int chi) {
     Context* ctx = T.ctx;
     long long m = prod(T.d, 0, ncod), n = prod(T.d, ncod);
     long long r = std::min(m, n), k = std::min<long long>(chi, r);
@@ -379,6 +379,121 @@ Trunc eigh_trunc(DT MM, int ncod, int chi) {
         ctx->ctr.subspace_fallbacks++;
     }
     return eigh_trunc_jacobi(std::move(MM), ncod, chi);
+}
+
+}  // namespace tnr
+
+// ---------------------------------------------------------------------------
+// Top-chi singular triplets of a large matrix (svd_trunc under truncrank when chi << min(m,n)):
+// block subspace iteration on the right singular subspace.  Each iteration is two DMMA GEMMs
+// (A Q and A^T U) and a one-sided Jacobi SVD of the thin m x b matrix A Q -- never of the Gram
+// matrix, so small singular values keep the absolute accuracy eps*sigma_1 of a direct SVD.
+// Certified by ||A^T u - sigma v|| <= 1e-13 sigma_1 on the kept triplets; otherwise the caller
+// falls back to the full Jacobi SVD.
+// ---------------------------------------------------------------------------
+namespace tnr {
+namespace {
+
+bool svd_topk(Context* ctx, const DT& T, long long m, long long n, long long k, Trunc& out) {
+    long long b = std::min(std::min(m, n), std::max(2 * k, k + 64));
+    b += (b & 1);
+    DT f2(ctx, {1});
+    sum_squares(ctx, T.p, m * n, f2.p);
+    DT Y0(ctx, {n, b});
+    fill_random(ctx, Y0.p, n * b, 0x5eedbeefULL);
+    DT Q = gram_orthonormalize(ctx, Y0, n, b);
+    Q = gram_orthonormalize(ctx, Q, n, b);
+    Y0.release();
+    std::vector<double> sig(b), rn(k), sc(b);
+    DT Us, X, Sg;
+    double best = 1e300;
+    bool certified = false;
+    int stalled = 0;
+    const int maxit = 120;
+    for (int it = 0; it < maxit; ++it) {
+        DT Y(ctx, {m, b});
+        gemm(ctx, 'N', 'N', (int)m, (int)b, (int)n, 1.0, T.p, m, Q.p, n, 0.0, Y.p, m);
+        DT W(ctx, {b, b});
+        set_identity(ctx, W.p, b);
+        jacobi_orthogonalize(ctx, Y.p, m, b, m, W.p, b);  // Y <- (A Q) W = U Sigma
+        DT vals(ctx, {b});
+        column_values(ctx, Y.p, m, b, m, nullptr, 0, vals.p, false);
+        IntBuf rank(ctx, b);
+        rank_select(ctx, vals.p, b, b, rank.p, nullptr);
+        DT Sn(ctx, {b});
+        gather_values(ctx, vals.p, b, rank.p, b, Sn.p, true);
+        DT Un(ctx, {m, b}), Wg(ctx, {b, b}), Xn(ctx, {n, b});
+        gather_columns(ctx, Y.p, m, b, m, rank.p, b, Un.p, m, vals.p, true);   // unit left vectors
+        gather_columns(ctx, W.p, b, b, b, rank.p, b, Wg.p, b, nullptr, false);
+        Y.release();
+        gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Q.p, n, Wg.p, b, 0.0, Xn.p, n);  // right
+        DT Z(ctx, {n, b});
+        gemm(ctx, 'T', 'N', (int)n, (int)b, (int)m, 1.0, T.p, m, Un.p, m, 0.0, Z.p, n);  // A^T U
+        DT R(ctx, {n, k});
+        TNR_CUDA(cudaMemcpyAsync(R.p, Xn.p, n * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        diag_scale(ctx, R.p, n, k, n, Sn.p, false, 0, 0.0);
+        scale(ctx, R.p, n * k, -1.0);
+        axpy(ctx, R.p, Z.p, 1.0, n * k);
+        DT rnd(ctx, {k});
+        column_values(ctx, R.p, n, k, n, nullptr, 0, rnd.p, false);
+        d2h(ctx, sig.data(), Sn.p, b);
+        d2h(ctx, rn.data(), rnd.p, k);
+        double smax = sig[0], res = 0.0;
+        for (long long j = 0; j < k; ++j) res = std::max(res, rn[j]);
+        res = (smax > 0.0) ? res / smax : 0.0;
+        if (!std::isfinite(res)) return false;
+        Us = std::move(Un);
+        X = std::move(Xn);
+        Sg = std::move(Sn);
+        if (res <= 1e-13) { certified = true; break; }
+        if (res > 0.7 * best) ++stalled; else stalled = 0;
+        best = std::min(best, res);
+        if (stalled >= 3 && best <= 2e-12) { certified = true; break; }
+        if (stalled >= 8) return false;
+        for (long long j = 0; j < b; ++j) sc[j] = (sig[j] > 1e-14 * smax) ? 1.0 / sig[j] : 0.0;
+        DT scd(ctx, {b});
+        h2d(ctx, scd.p, sc.data(), b);
+        diag_scale(ctx, Z.p, n, b, n, scd.p, false, 0, 0.0);
+        Q = gram_orthonormalize(ctx, Z, n, b);
+    }
+    if (!certified) return false;
+    if (!(sig[k - 1] > 1e-13 * sig[0])) return false;  // numerically rank deficient: exact path
+    TNR_CUDA(cudaMemcpyAsync(out.U.p, Us.p, m * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    TNR_CUDA(cudaMemcpyAsync(out.S.p, Sg.p, k * sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    long long dd[2] = {n, k};
+    int pp[2] = {1, 0};
+    permute(ctx, X.p, out.Vt.p, 2, dd, pp);  // first k columns of X, transposed -> k x n
+    double F2 = 0.0, kept = 0.0, mid = 0.0;
+    d2h(ctx, &F2, f2.p, 1);
+    for (long long j = 0; j < b; ++j) (j < k ? kept : mid) += sig[j] * sig[j];
+    double eps = std::sqrt(mid + std::max(0.0, F2 - kept - mid));
+    h2d(ctx, out.eps.p, &eps, 1);
+    ctx->ctr.subspace_svd++;
+    return true;
+}
+
+}  // namespace
+
+Trunc svd_trunc(const DT& T, int ncod, int chi) {
+    Context* ctx = T.ctx;
+    long long m = prod(T.d, 0, ncod), n = prod(T.d, ncod);
+    long long r = std::min(m, n), k = std::min<long long>(chi, r);
+    if (!ctx->disable_subspace && r >= 1024 && std::max(2 * k, k + 64) <= r / 4) {
+        Dims cod(T.d.begin(), T.d.begin() + ncod), dom(T.d.begin() + ncod, T.d.end());
+        Trunc out;
+        Dims ud = cod; ud.push_back(k);
+        Dims vd = {k}; vd.insert(vd.end(), dom.begin(), dom.end());
+        out.U = DT(ctx, ud);
+        out.S = DT(ctx, {k});
+        out.Vt = DT(ctx, vd);
+        out.eps = DT(ctx, {1});
+        if (svd_topk(ctx, T, m, n, k, out)) return out;
+        ctx->ctr.subspace_fallbacks++;
+    }
+    return svd_trunc_jacobi(T, ncod, chi);
 }
 
 }  // namespace tnr
