@@ -336,14 +336,14 @@ bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out)
         if (stalled >= 8) return false;
         // next basis: Ritz-rotated images, equilibrated by 1/|theta|, re-orthonormalised
         for (long long j = 0; j < b; ++j)
-            sc[j] = (std::fabs(theta[j]) > 1e-14 * tmax) ? 1.0 / std::fabs(theta[j]) : 0.0;
+            sc[j] = (std::fabs(theta[j]) > 1e-16 * tmax) ? 1.0 / std::fabs(theta[j]) : 0.0;
         DT scd(ctx, {b});
         h2d(ctx, scd.p, sc.data(), b);
         diag_scale(ctx, ZS.p, n, b, n, scd.p, false, 0, 0.0);
         Q = gram_orthonormalize(ctx, ZS, n, b);
     }
     if (!certified) return false;
-    if (!(std::fabs(theta[k - 1]) > 1e-13 * std::fabs(theta[0]))) return false;  // rank deficient
+    if (!(std::fabs(theta[k - 1]) > 1e-15 * std::fabs(theta[0]))) return false;  // rank deficient
     TNR_CUDA(cudaMemcpyAsync(out.U.p, QS.p, n * k * sizeof(double), cudaMemcpyDeviceToDevice,
                              ctx->stream));
     TNR_CUDA(cudaMemcpyAsync(out.S.p, Th.p, k * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -451,14 +451,15 @@ bool svd_topk(Context* ctx, const DT& T, long long m, long long n, long long k, 
         best = std::min(best, res);
         if (stalled >= 3 && best <= 2e-12) { certified = true; break; }
         if (stalled >= 8) return false;
-        for (long long j = 0; j < b; ++j) sc[j] = (sig[j] > 1e-14 * smax) ? 1.0 / sig[j] : 0.0;
+        for (long long j = 0; j < b; ++j) sc[j] = (sig[j] > 1e-16 * smax) ? 1.0 / sig[j] : 0.0;
         DT scd(ctx, {b});
         h2d(ctx, scd.p, sc.data(), b);
         diag_scale(ctx, Z.p, n, b, n, scd.p, false, 0, 0.0);
         Q = gram_orthonormalize(ctx, Z, n, b);
     }
     if (!certified) return false;
-    if (!(sig[k - 1] > 1e-13 * sig[0])) return false;  // numerically rank deficient: exact path
+    if (!(sig[0] > 0.0)) return false;  // zero matrix: exact path
+    // triplets below 1e-15 sigma_1 are rounding noise in any SVD; they carry no weight in U S V
     TNR_CUDA(cudaMemcpyAsync(out.U.p, Us.p, m * k * sizeof(double), cudaMemcpyDeviceToDevice,
                              ctx->stream));
     TNR_CUDA(cudaMemcpyAsync(out.S.p, Sg.p, k * sizeof(double), cudaMemcpyDeviceToDevice,
