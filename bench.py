@@ -297,6 +297,11 @@ def run_gpu(args):
                 "step_tflops": (fl / sec / 1e12) if fl else None,
                 "step_frac_of_fp64_peak": (fl / sec / 1e12 / peak / world) if fl else None,
                 "norms_tail": norms[-min(3, len(norms)):],
+                # size-independent sanity at the full workload: free energy of the run so far
+                # (series sum_i log(z_i) 8^(1-i), remainder < 8^-n) against the value the
+                # reference tests against (test/schemes.jl:11, f = -3.507, rtol 1e-3)
+                "free_energy": tk.free_energy(norms, tk.ising_βc_3D, scalefactor=8.0),
+                "free_energy_benchmark": -3.507,
                 "wall_s_timed_region": wall,
             },
             "roofline": {

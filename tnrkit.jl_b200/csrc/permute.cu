@@ -66,24 +66,34 @@ __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restric
     double* dp = dst + doff + i0 * p.si_d + j0 * p.sj_d + b0 * p.sb_d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = TI + 1, slab = TJ * pitch;
-    // read: one warp per (j, b) row, lanes along i (source contiguous)
-    const int rrows = nj * nb;
-#pragma unroll 4
-    for (int row = warp; row < rrows; row += 8) {
-        int j = row % nj, b = row / nj;
-        const double* g = sp + j * p.sj_s + b * p.sb_s;
-        double* t = tile + b * slab + j * pitch;
-        for (int i = lane; i < ni; i += 32) t[i] = g[i * p.si_s];
+    // read: one warp per (j, b) row, lanes along i (source contiguous).  No div/mod in the
+    // loops: (b, j) advance by pointer increments.
+    const long long lane_s = lane * p.si_s, step_s = 32 * p.si_s;
+    for (int b = 0; b < nb; ++b) {
+        const double* gb = sp + b * p.sb_s + lane_s;
+        double* tb_ = tile + b * slab;
+#pragma unroll 3
+        for (int j = warp; j < nj; j += 8) {
+            const double* g = gb + j * p.sj_s;
+            double* t = tb_ + j * pitch;
+            long long off = 0;
+            for (int i = lane; i < ni; i += 32, off += step_s) t[i] = g[off];
+        }
     }
     __syncthreads();
     // write: one warp per (i, b) row, lanes along j (destination contiguous)
-    const int wrows = ni * nb;
-#pragma unroll 4
-    for (int row = warp; row < wrows; row += 8) {
-        int i = row % ni, b = row / ni;
-        double* g = dp + i * p.si_d + b * p.sb_d;
-        const double* t = tile + b * slab + i;
-        for (int j = lane; j < nj; j += 32) g[j * p.sj_d] = t[j * pitch];
+    const long long lane_d = lane * p.sj_d, step_d = 32 * p.sj_d;
+    for (int b = 0; b < nb; ++b) {
+        double* gb = dp + b * p.sb_d + lane_d;
+        const double* tb_ = tile + b * slab + lane * pitch;
+#pragma unroll 3
+        for (int i = warp; i < ni; i += 8) {
+            double* g = gb + i * p.si_d;
+            const double* t = tb_ + i;
+            long long off = 0;
+            int toff = 0;
+            for (int j = lane; j < nj; j += 32, off += step_d, toff += 32 * pitch) g[off] = t[toff];
+        }
     }
 }
 
