@@ -24,30 +24,31 @@ struct CopyParams {
     long long dims[MAXR];
     long long ss[MAXR];
     long long ds[MAXR];
-    // tile dims (tiled kernel) / inner dim (row kernel)
-    long long ni, si_s, si_d;  // src-fastest dim: extent, src stride, dst stride
-    long long nj, sj_s, sj_d;  // dst-fastest dim
-    long long tiles_i, tiles_j;
-    int ti, tj;                // tile extents along i and j
-    // slice batch: nb consecutive values of a third index per block
-    long long nbdim, sb_s, sb_d, tiles_b;
-    int nb;
-    long long total;           // total elements (row kernel)
+    // row kernel: inner dim
+    long long ni, si_s, si_d;
+    long long total;
+    // tiled kernel: composite source-contiguous index i' = (i1, i2) and composite
+    // destination-contiguous index j' = (j1, j2)
+    long long n_i1, n_i2, n_j1, n_j2;          // full extents
+    long long s_i1, d_i1, d_i2, s_i2;          // strides of i1 / i2 (src, dst)
+    long long d_j1, s_j1, s_j2, d_j2;          // strides of j1 / j2
+    int TI1, TI2, TJ1, TJ2;                    // tile extents
+    long long tiles_i1, tiles_i2, tiles_j1, tiles_j2;
+    int pitch;
 };
 
-constexpr int TMAX = 48;
-
+// Tile = (i1 x i2) x (j1 x j2): reads run along the source-contiguous composite i', writes along
+// the destination-contiguous composite j' (e.g. 96-element = 768-byte runs on both sides for
+// bond dimension 24), transposed through shared memory with an odd pitch (conflict free).
 __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restrict__ src,
                                                          double* __restrict__ dst,
                                                          const CopyParams p) {
-    extern __shared__ double tile[];  // [nb][TJ][TI + 1]
+    extern __shared__ double tile[];  // [TJ1*TJ2][pitch]
     long long bid = blockIdx.x;
-    long long ti = bid % p.tiles_i;
-    bid /= p.tiles_i;
-    long long tj = bid % p.tiles_j;
-    bid /= p.tiles_j;
-    long long tb = bid % p.tiles_b;
-    bid /= p.tiles_b;
+    long long t_i1 = bid % p.tiles_i1; bid /= p.tiles_i1;
+    long long t_i2 = bid % p.tiles_i2; bid /= p.tiles_i2;
+    long long t_j1 = bid % p.tiles_j1; bid /= p.tiles_j1;
+    long long t_j2 = bid % p.tiles_j2; bid /= p.tiles_j2;
     long long soff = 0, doff = 0;
 #pragma unroll
     for (int d = 0; d < MAXR; ++d) {
@@ -58,41 +59,44 @@ __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restric
             doff += i * p.ds[d];
         }
     }
-    const int TI = p.ti, TJ = p.tj;
-    const long long i0 = ti * TI, j0 = tj * TJ, b0 = tb * p.nb;
-    const int ni = (int)min((long long)TI, p.ni - i0), nj = (int)min((long long)TJ, p.nj - j0);
-    const int nb = (int)min((long long)p.nb, p.nbdim - b0);
-    const double* sp = src + soff + i0 * p.si_s + j0 * p.sj_s + b0 * p.sb_s;
-    double* dp = dst + doff + i0 * p.si_d + j0 * p.sj_d + b0 * p.sb_d;
+    const long long i10 = t_i1 * p.TI1, i20 = t_i2 * p.TI2, j10 = t_j1 * p.TJ1, j20 = t_j2 * p.TJ2;
+    const int ti1 = (int)min((long long)p.TI1, p.n_i1 - i10);
+    const int ti2 = (int)min((long long)p.TI2, p.n_i2 - i20);
+    const int tj1 = (int)min((long long)p.TJ1, p.n_j1 - j10);
+    const int tj2 = (int)min((long long)p.TJ2, p.n_j2 - j20);
+    const int ci = ti1 * ti2, cj = tj1 * tj2;   // composite extents of this tile
+    const double* sp = src + soff + i10 * p.s_i1 + i20 * p.s_i2 + j10 * p.s_j1 + j20 * p.s_j2;
+    double* dp = dst + doff + i10 * p.d_i1 + i20 * p.d_i2 + j10 * p.d_j1 + j20 * p.d_j2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pitch = TI + 1, slab = TJ * pitch;
-    // read: one warp per (j, b) row, lanes along i (source contiguous).  No div/mod in the
-    // loops: (b, j) advance by pointer increments.
-    const long long lane_s = lane * p.si_s, step_s = 32 * p.si_s;
-    for (int b = 0; b < nb; ++b) {
-        const double* gb = sp + b * p.sb_s + lane_s;
-        double* tb_ = tile + b * slab;
-#pragma unroll 3
-        for (int j = warp; j < nj; j += 8) {
-            const double* g = gb + j * p.sj_s;
-            double* t = tb_ + j * pitch;
+    const int pitch = p.pitch;
+    // read phase: one warp per j' row, lanes along the source-contiguous composite i'
+    {
+        const long long lane_s = lane * p.s_i1, step_s = 32 * p.s_i1;
+        int j1 = warp % tj1, j2 = warp / tj1;          // one div per warp, then increments
+        const int dj1 = 8 % tj1, dj2 = 8 / tj1;
+        for (int r = warp; r < cj; r += 8) {
+            const double* g = sp + j1 * p.s_j1 + j2 * p.s_j2 + lane_s;
+            double* t = tile + r * pitch;
             long long off = 0;
-            for (int i = lane; i < ni; i += 32, off += step_s) t[i] = g[off];
+            for (int i = lane; i < ci; i += 32, off += step_s) t[i] = g[off];
+            j1 += dj1; j2 += dj2;
+            if (j1 >= tj1) { j1 -= tj1; ++j2; }
         }
     }
     __syncthreads();
-    // write: one warp per (i, b) row, lanes along j (destination contiguous)
-    const long long lane_d = lane * p.sj_d, step_d = 32 * p.sj_d;
-    for (int b = 0; b < nb; ++b) {
-        double* gb = dp + b * p.sb_d + lane_d;
-        const double* tb_ = tile + b * slab + lane * pitch;
-#pragma unroll 3
-        for (int i = warp; i < ni; i += 8) {
-            double* g = gb + i * p.si_d;
-            const double* t = tb_ + i;
+    // write phase: one warp per i' row, lanes along the destination-contiguous composite j'
+    {
+        const long long lane_d = lane * p.d_j1, step_d = 32 * p.d_j1;
+        int i1 = warp % ti1, i2 = warp / ti1;
+        const int di1 = 8 % ti1, di2 = 8 / ti1;
+        for (int r = warp; r < ci; r += 8) {
+            double* g = dp + i1 * p.d_i1 + i2 * p.d_i2 + lane_d;
+            const double* t = tile + lane * pitch + r;
             long long off = 0;
             int toff = 0;
-            for (int j = lane; j < nj; j += 32, off += step_d, toff += 32 * pitch) g[off] = t[toff];
+            for (int j = lane; j < cj; j += 32, off += step_d, toff += 32 * pitch) g[off] = t[toff];
+            i1 += di1; i2 += di2;
+            if (i1 >= ti1) { i1 -= ti1; ++i2; }
         }
     }
 }
@@ -184,38 +188,52 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         p.total = total;
         copy_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, p);
     } else {
-        p.ni = m[js].n; p.si_s = m[js].s; p.si_d = m[js].d;
-        p.nj = m[0].n; p.sj_s = m[0].s; p.sj_d = m[0].d;
-        p.ti = p.ni <= TMAX ? (int)p.ni : 32;
-        p.tj = p.nj <= TMAX ? (int)p.nj : 32;
-        // batch index: the remaining group with the smallest source stride (keeps the reads
-        // of one block inside few DRAM pages); batch size targets <= 40 KB of shared memory
-        size_t jb = (size_t)-1;
-        for (size_t i = 1; i < m.size(); ++i) {
-            if (i == js) continue;
-            if (jb == (size_t)-1 || m[i].s < m[jb].s) jb = i;
-        }
-        const long long slab_bytes = (long long)p.tj * (p.ti + 1) * 8;
-        if (jb != (size_t)-1) {
-            p.nbdim = m[jb].n; p.sb_s = m[jb].s; p.sb_d = m[jb].d;
-            p.nb = (int)std::max<long long>(1, std::min<long long>(p.nbdim, 40960 / slab_bytes));
-        } else {
-            p.nbdim = 1; p.sb_s = 0; p.sb_d = 0; p.nb = 1;
-        }
-        p.tiles_b = (p.nbdim + p.nb - 1) / p.nb;
+        // i1 = source-fastest group, j1 = destination-fastest group (m[0]); i2 / j2 = the
+        // groups that continue them contiguously in the source / destination, if any
+        const size_t none = (size_t)-1;
+        size_t i2 = none, j2 = none;
+        for (size_t i = 1; i < m.size(); ++i)
+            if (i != js && m[i].s == m[js].s * m[js].n) i2 = i;
+        for (size_t i = 1; i < m.size(); ++i)
+            if (i != js && i != i2 && m[i].d == m[0].d * m[0].n) j2 = i;
+        const int TGT = 96;  // composite run length (doubles)
+        auto split = [&](long long n1, long long n2, int& T1, int& T2) {
+            if (n1 >= TGT) { T1 = TGT; T2 = 1; }
+            else if (n1 > 48 || n2 <= 1) { T1 = (int)std::min<long long>(n1, 48); T2 = 1;
+                                           if (n1 <= TGT) T1 = (int)n1; }
+            else { T1 = (int)n1; T2 = (int)std::max<long long>(1, std::min<long long>(n2, TGT / n1)); }
+        };
+        p.n_i1 = m[js].n; p.s_i1 = m[js].s; p.d_i1 = m[js].d;
+        p.n_j1 = m[0].n;  p.s_j1 = m[0].s;  p.d_j1 = m[0].d;
+        p.n_i2 = (i2 != none) ? m[i2].n : 1; p.s_i2 = (i2 != none) ? m[i2].s : 0;
+        p.d_i2 = (i2 != none) ? m[i2].d : 0;
+        p.n_j2 = (j2 != none) ? m[j2].n : 1; p.s_j2 = (j2 != none) ? m[j2].s : 0;
+        p.d_j2 = (j2 != none) ? m[j2].d : 0;
+        split(p.n_i1, p.n_i2, p.TI1, p.TI2);
+        split(p.n_j1, p.n_j2, p.TJ1, p.TJ2);
+        p.tiles_i1 = (p.n_i1 + p.TI1 - 1) / p.TI1;
+        p.tiles_i2 = (p.n_i2 + p.TI2 - 1) / p.TI2;
+        p.tiles_j1 = (p.n_j1 + p.TJ1 - 1) / p.TJ1;
+        p.tiles_j2 = (p.n_j2 + p.TJ2 - 1) / p.TJ2;
+        p.pitch = p.TI1 * p.TI2 + 1;
+        if ((p.pitch & 1) == 0) p.pitch += 1;
         p.rank = 0;
         long long outer = 1;
         for (size_t i = 1; i < m.size(); ++i) {
-            if (i == js || i == jb) continue;
+            if (i == js || i == i2 || i == j2) continue;
             p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
             p.rank++;
             outer *= m[i].n;
         }
-        p.tiles_i = (p.ni + p.ti - 1) / p.ti;
-        p.tiles_j = (p.nj + p.tj - 1) / p.tj;
-        long long blocks = p.tiles_i * p.tiles_j * p.tiles_b * outer;
+        long long blocks = p.tiles_i1 * p.tiles_i2 * p.tiles_j1 * p.tiles_j2 * outer;
         TNR_CHECK(blocks < (1LL << 31), "strided_copy: grid too large");
-        size_t smem = (size_t)p.nb * slab_bytes;
+        size_t smem = (size_t)p.TJ1 * p.TJ2 * p.pitch * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            TNR_CUDA(cudaFuncSetAttribute(copy_tiled_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured = true;
+        }
         copy_tiled_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
     }
     TNR_CUDA(cudaGetLastError());
