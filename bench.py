@@ -306,7 +306,12 @@ def run_gpu(args):
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE 13824^3 launch of this
+                # kernel (ncu --set full, gpurun_out/prof_gemm_tma_13824_r01.ncu-rep, summarised
+                # in profiles/r01_summary.md): 32.13 GB + 1.53 GB for 4.59 GB of operand+result
+                # bytes (operands re-read from L2, hit rate 81 %); 227 GB/s, 3 % of HBM
+                "traffic": 33.66e9 if chi == 24 else None, "traffic_unit": "bytes per launch",
                 "kernel": "gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
                           "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
                           "projector Gram GEMMs above 1e11 flop)", "launches_timed": gemm_n,
