@@ -71,7 +71,7 @@ def test_sym_svd_global_truncation(tk, N, chi):
     assert np.abs(rec - best).max() <= 1e-10 * sref[0]
 
 
-@pytest.mark.parametrize("name,chi,n", [("TRG", 8, 6), ("BTRG", 8, 6)])
+@pytest.mark.parametrize("name,chi,n", [("TRG", 8, 6), ("BTRG", 8, 6), ("HOTRG", 6, 4), ("ATRG", 8, 4)])
 @pytest.mark.parametrize("model", ["ising_z2", "potts_z3"])
 def test_block_sparse_schemes_match_oracle_and_dense(tk, name, chi, n, model):
     T = tk.classical_ising() if model == "ising_z2" else tk.classical_potts(3)

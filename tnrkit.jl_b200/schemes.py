@@ -143,16 +143,44 @@ class TRG(_SymmetricMixin, TNRScheme):
         return n
 
 
-class HOTRG(TNRScheme):
+class _Sym2D(_SymmetricMixin, TNRScheme):
+    """2D schemes whose step! also exists on block-sparse Z_N tensors."""
+    _sym_step = None
+
+    def __init__(self, T, ctx=None, symmetric=None):
+        if not self._init_sym(T, symmetric, ctx):
+            TNRScheme.__init__(self, T, ctx)
+
+    def step(self, trunc):
+        if not self.sym:
+            return TNRScheme.step(self, trunc)
+        from . import symmetric
+
+        self.T = getattr(symmetric, self._sym_step)(self.T, _chi(trunc))
+        return self
+
+    def finalize(self):
+        if not self.sym:
+            return TNRScheme.finalize(self)
+        from .symmetric import sym_trace_2d
+
+        n = abs(sym_trace_2d(self.T))
+        self.T.scale(1.0 / n)
+        return n
+
+
+class HOTRG(_Sym2D):
     """Higher-Order TRG (hotrg.jl)."""
     kind = _lib.TNR_HOTRG
     _step_fn = "tnr_hotrg_step"
+    _sym_step = "hotrg_step_sym"
 
 
-class ATRG(TNRScheme):
+class ATRG(_Sym2D):
     """Anisotropic TRG (atrg.jl)."""
     kind = _lib.TNR_ATRG
     _step_fn = "tnr_atrg_step"
+    _sym_step = "atrg_step_sym"
 
 
 class ATRG_3D(TNRScheme):

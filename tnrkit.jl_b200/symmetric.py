@@ -381,3 +381,129 @@ def btrg_step_sym(T: SymTensor, S1, S2, k: float, chi: int):
 
 def identity_weights(leg: Leg, ctx):
     return {q: DeviceTensor.from_numpy(np.ones(d), 1, ctx) for q, d in leg.dims.items()}
+
+
+# ------------------------------------------------------------------------------------
+# HOTRG / ATRG on block-sparse tensors
+# ------------------------------------------------------------------------------------
+def sym_conj(T: SymTensor) -> SymTensor:
+    """conj(T) of a real Z_N tensor: same block data, every arrow reversed (dual spaces)."""
+    return SymTensor(T.N, [l.flipped() for l in T.legs], dict(T.blocks), T.ctx)
+
+
+def sym_clone(T: SymTensor) -> SymTensor:
+    return SymTensor(T.N, list(T.legs), {k: b.clone() for k, b in T.blocks.items()}, T.ctx)
+
+
+def sym_eigh_trunc(MM: SymTensor, ncod: int, chi: int):
+    """eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) per coupled sector with a
+    sector-global choice of the chi eigenvalues of largest magnitude.
+    Returns U [cod..., bond(-)], W {c: DeviceTensor}, eps."""
+    import torch
+
+    from .tensor import eigh_trunc
+
+    ctx = MM.ctx
+    rows, cols = list(range(ncod)), list(range(ncod, len(MM.legs)))
+    mats, rt, _ = MM.matricize(rows, cols)
+    fac, order, eps2 = {}, sorted(mats), 0.0
+    for c in order:
+        n = mats[c].dims[0]
+        assert mats[c].dims[1] == n, "eigh_trunc: sector blocks must be square"
+        W, V, e = eigh_trunc(mats[c], chi)
+        fac[c] = (W, V)
+        eps2 += e * e
+    allW = torch.cat([fac[c][0].buf[: fac[c][0].size] for c in order])
+    n = allW.numel()
+    ranks = (C.c_int32 * n)()
+    e_sel = C.c_double()
+    ctx.call("tnr_topk_select", C.c_void_p(allW.data_ptr()), n, chi, ranks, C.byref(e_sel))
+    eps = math.sqrt(eps2 + e_sel.value ** 2)
+    bond, pos = {}, 0
+    for c in order:
+        ns = fac[c][0].size
+        k = sum(1 for j in range(pos, pos + ns) if ranks[j] < chi)
+        pos += ns
+        if k > 0:
+            bond[c] = k
+    U = SymTensor(MM.N, [MM.legs[i] for i in rows] + [Leg(bond, -1)], {}, ctx)
+    Wd = {}
+    for c, k in bond.items():
+        W, V = fac[c]
+        Wd[c] = DeviceTensor(W.buf[:k].clone(), (k,), 1, ctx)
+        nr = mats[c].dims[0]
+        for key, roff, size in rt[c]:
+            bd = tuple(MM.legs[i].dims[q] for i, q in zip(rows, key)) + (k,)
+            blk = DeviceTensor.empty(bd, None, ctx)
+            src = C.c_void_p(V.buf.data_ptr() + 8 * roff)
+            ctx.call("tnr_strided_copy", src, blk.ptr, 2, _lib.i64((size, k)), _lib.i64((1, nr)),
+                     _lib.i64((1, size)))
+            U.blocks[key + (c,)] = blk
+    return U, Wd, eps
+
+
+def _hotrg_proj_sym(mm_left, mm_right, chi):
+    """`_, U, eps = eigh_trunc!(MM); ...; if eps > eps' then U', eps'` (hotrg.jl:106-118)."""
+    U, _, e = sym_eigh_trunc(mm_left, 2, chi)
+    U2, _, e2 = sym_eigh_trunc(mm_right, 2, chi)
+    return U2 if e > e2 else U
+
+
+def hotrg_step_sym(T: SymTensor, chi: int) -> SymTensor:
+    """step!(::HOTRG) on a Z_N tensor -- src/schemes/hotrg.jl:155-161."""
+    Tc = sym_conj(T)
+    # x projector (hotrg.jl:102-114), A1 = A2 = T
+    X = sym_contract(T, "aeij", Tc, "cfij", "aecf")
+    Y = sym_contract(T, "bkel", Tc, "dkfl", "bedf")
+    ML = sym_contract(X, "aecf", Y, "bedf", "abcd")
+    X = sym_contract(Tc, "jeia", T, "jfic", "eafc")
+    Y = sym_contract(Tc, "lkeb", T, "lkfd", "ebfd")
+    MR = sym_contract(X, "eafc", Y, "ebfd", "abcd")
+    Ux = _hotrg_proj_sym(ML, MR, chi)
+    # T := conj(Ux[1 2;-1]) Ux[3 4;-4] A2[1 5;-3 3] A1[2 -2;5 4]   (hotrg.jl:57-58)
+    W = sym_contract(sym_conj(Ux), "ija", T, "imck", "jamck")
+    W = sym_contract(W, "jamck", T, "jbml", "ackbl")
+    T1 = sym_contract(W, "ackbl", Ux, "kld", "abcd")
+    T1c = sym_conj(T1)
+    # y projector (hotrg.jl:137-149)
+    X = sym_contract(T1, "iaje", T1c, "icjf", "aecf")
+    Y = sym_contract(T1, "ebkl", T1c, "fdkl", "ebfd")
+    ML = sym_contract(X, "aecf", Y, "ebfd", "abcd")
+    X = sym_contract(T1c, "ijae", T1, "ijcf", "aecf")
+    Y = sym_contract(T1c, "ekbl", T1, "fkdl", "ebfd")
+    MR = sym_contract(X, "aecf", Y, "ebfd", "abcd")
+    Uy = _hotrg_proj_sym(ML, MR, chi)
+    # T := A1[-1 1;3 5] A2[5 2;4 -4] conj(Uy[1 2;-2]) Uy[3 4;-3]   (hotrg.jl:79-80)
+    W = sym_contract(T1, "aikm", sym_conj(Uy), "ijb", "akmjb")
+    W = sym_contract(W, "akmjb", T1, "mjld", "akbld")
+    return sym_contract(W, "akbld", Uy, "klc", "abcd")
+
+
+def _atrg_half_sym(T: SymTensor, chi: int) -> SymTensor:
+    """_step!(::ATRG) on a Z_N tensor -- src/schemes/atrg.jl:47-82."""
+    A, S, B, _ = sym_svd_trunc(T.permute((0, 2, 1, 3)), 2, chi)   # A [i1 i3 k], B [k i2 i4]
+    Cc, D = sym_clone(A), sym_clone(B)
+    Bs = sym_clone(B).scale_leg(0, S)
+    Cc.scale_leg(2, S)
+    # M[-1 -2;-3 -4] := B[-3;1 -4] * C[-1 1;-2]; SVD of permute(M, ((1,3),(2,4))) = [a c b d]
+    M = sym_contract(Cc, "aib", Bs, "cid", "acbd")
+    X, S2, Y, _ = sym_svd_trunc(M, 2, chi)
+    rs = vec_map(S2, 1)
+    X.scale_leg(2, rs)
+    Y.scale_leg(0, rs)
+    # Q[-1 -2;-3 -4] := A[3 -3;2] * D[1;-2 4] * X[4 2;-4] * Y[-1 1;3]
+    AX = sym_contract(A, "kcj", X, "ljd", "kcld")
+    YD = sym_contract(Y, "aik", D, "ibl", "akbl")
+    Q = sym_contract(YD, "akbl", AX, "kcld", "abcd")
+    H, S3, G, _ = sym_svd_trunc(Q, 2, chi)
+    rs = vec_map(S3, 1)
+    H.scale_leg(2, rs)
+    G.scale_leg(0, rs)
+    # T[-1 -2;-3 -4] := G[-1;-3 1] * H[1 -2;-4]
+    return sym_contract(G, "aci", H, "ibd", "abcd")
+
+
+def atrg_step_sym(T: SymTensor, chi: int) -> SymTensor:
+    """step!(::ATRG) on a Z_N tensor -- src/schemes/atrg.jl:37-45."""
+    T = _atrg_half_sym(T, chi).permute((1, 3, 0, 2))
+    return _atrg_half_sym(T, chi).permute((2, 0, 3, 1))
