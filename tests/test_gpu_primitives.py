@@ -221,3 +221,29 @@ def test_svd_trunc_subspace_path(tk, ctx, m, n, chi, decay):
     best = (uu[:, :chi] * ss[:chi]) @ vv[:chi]
     gap = sref[chi - 1] - sref[chi]
     assert np.abs((u * s) @ vt - best).max() <= 1e-13 * sref[0] ** 2 / gap * 50
+
+
+@pytest.mark.parametrize("opt", ["disable_block_jacobi", "disable_precondition"])
+def test_jacobi_variants_agree(tk, ctx, opt):
+    """Shared-memory block rounds / Gram preconditioning of tall problems are pure speed-ups:
+    switching them off must give the same factorisations."""
+    rng = np.random.default_rng(11)
+    tall = rng.standard_normal((2000, 96)) * np.logspace(0, -9, 96)[None, :]
+    sq = rng.standard_normal((200, 200))
+    sq = sq @ sq.T * 1e-3
+    res = {}
+    for flag in (0, 1):
+        ctx.set_option(opt, flag)
+        try:
+            U, S, Vt, eps = tk.svd_trunc(_up(tk, tall), 1, 40)
+            W, V, e2 = tk.eigh_trunc(_up(tk, sq), 30)
+            res[flag] = (S.to_numpy(), (U.to_numpy() * S.to_numpy()) @ Vt.to_numpy(), eps,
+                         W.to_numpy(), e2)
+        finally:
+            ctx.set_option(opt, 0)
+    sref = np.linalg.svd(tall, compute_uv=False)
+    for flag in (0, 1):
+        assert np.abs(res[flag][0] - sref[:40]).max() <= 1e-12 * sref[0]
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-11 * sref[0]
+    assert abs(res[0][2] - res[1][2]) <= 1e-12 * sref[0]
+    assert np.abs(res[0][3] - res[1][3]).max() <= 1e-12 * np.abs(res[0][3]).max()

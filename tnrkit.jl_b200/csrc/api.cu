@@ -138,6 +138,8 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
     return guard(ctx, [&] {
         if (std::strcmp(key, "disable_tma") == 0) ctx->c.disable_tma = value != 0;
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
+        else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
+        else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
         else throw Error(1, std::string("unknown option: ") + key);
     });
 }
@@ -554,6 +556,7 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "gemm_launches") *value = (double)c.gemm_launches;
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;

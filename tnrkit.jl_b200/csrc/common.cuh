@@ -35,6 +35,7 @@ struct Counters {
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
     unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
+    unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi
@@ -52,6 +53,8 @@ struct Context {
     bool time_gemm = false;
     bool disable_tma = false;  // force the cp.async GEMM (A/B testing)
     bool disable_subspace = false;  // force full Jacobi in eigh_trunc
+    bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
+    bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     std::string last_error;

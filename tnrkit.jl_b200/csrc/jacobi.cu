@@ -101,6 +101,90 @@ __global__ void __launch_bounds__(NT) jacobi_round_kernel(double* __restrict__ G
     }
 }
 
+// Block variant for matrices whose column pairs fit in shared memory: one CTA owns a PAIR OF
+// COLUMN BLOCKS (2*BC columns of G and of V), performs a complete cyclic sweep over all
+// 2BC(2BC-1)/2 column pairs inside shared memory (inner round-robin, one warp per pair, warp
+// shuffle reductions for the three dot products) and writes the columns back.  A sweep over the
+// matrix then needs n/BC - 1 launches instead of n - 1, and every rotation works on shared
+// memory instead of L2.
+template <int BC>
+__global__ void __launch_bounds__(256) jacobi_block_round_kernel(
+    double* __restrict__ G, int m, int n, long long ldg, double* __restrict__ V, int nv,
+    long long ldv, int round, int nblk_pad, double tol, double floor2, int* rot_count) {
+    extern __shared__ double sm[];
+    constexpr int NC = 2 * BC;
+    const int rows = m + (V ? nv : 0);       // G column followed by V column
+    double* cols = sm;                        // [NC][rows]
+    __shared__ int colid[NC];
+    int i = blockIdx.x, a, b;
+    if (i == 0) { a = nblk_pad - 1; b = round; }
+    else { a = (round + i) % (nblk_pad - 1); b = (round - i + nblk_pad - 1) % (nblk_pad - 1); }
+    const int bp = min(a, b), bq = max(a, b);
+    if (threadIdx.x < NC) {
+        int c = threadIdx.x < BC ? bp * BC + threadIdx.x : bq * BC + (threadIdx.x - BC);
+        colid[threadIdx.x] = (c < n) ? c : -1;
+    }
+    __syncthreads();
+    // load
+    for (int c = 0; c < NC; ++c) {
+        int gc = colid[c];
+        if (gc < 0) continue;
+        const double* g = G + (long long)gc * ldg;
+        double* d = cols + (long long)c * rows;
+        for (int r = threadIdx.x; r < m; r += 256) d[r] = g[r];
+        if (V) {
+            const double* v = V + (long long)gc * ldv;
+            for (int r = threadIdx.x; r < nv; r += 256) d[m + r] = v[r];
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int rotated = 0;
+    for (int rr = 0; rr < NC - 1; ++rr) {
+        for (int pi = warp; pi < BC; pi += 8) {
+            int x, y;
+            if (pi == 0) { x = NC - 1; y = rr; }
+            else { x = (rr + pi) % (NC - 1); y = (rr - pi + NC - 1) % (NC - 1); }
+            int p = min(x, y), q = max(x, y);
+            if (colid[p] < 0 || colid[q] < 0) continue;
+            double* cp = cols + (long long)p * rows;
+            double* cq = cols + (long long)q * rows;
+            double al = 0.0, be = 0.0, ga = 0.0;
+            for (int r = lane; r < m; r += 32) {
+                double u = cp[r], w = cq[r];
+                al += u * u; be += w * w; ga += u * w;
+            }
+            al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+            bool rot = (fabs(ga) > tol * sqrt(al * be)) && (al > floor2) && (be > floor2);
+            if (rot) {
+                double zeta = (be - al) / (2.0 * ga);
+                double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int r = lane; r < rows; r += 32) {
+                    double u = cp[r], w = cq[r];
+                    cp[r] = c * u - s * w;
+                    cq[r] = s * u + c * w;
+                }
+                if (lane == 0) ++rotated;
+            }
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && rotated) atomicAdd(rot_count, rotated);
+    // store
+    for (int c = 0; c < NC; ++c) {
+        int gc = colid[c];
+        if (gc < 0) continue;
+        double* g = G + (long long)gc * ldg;
+        const double* d = cols + (long long)c * rows;
+        for (int r = threadIdx.x; r < m; r += 256) g[r] = d[r];
+        if (V) {
+            double* v = V + (long long)gc * ldv;
+            for (int r = threadIdx.x; r < nv; r += 256) v[r] = d[m + r];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) frob2_kernel(const double* __restrict__ G, long long m,
                                                     long long n, long long ldg, double* out) {
     __shared__ double red[256];
@@ -206,7 +290,8 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
     double* d_f2 = dalloc(ctx, 1);
     int* d_rot;
     TNR_CUDA(cudaMallocAsync((void**)&d_rot, sizeof(int), ctx->stream));
-    frob2_kernel<<<1, 256, 0, ctx->stream>>>(G, m, n, ldg, d_f2);
+    if (ldg == m) sum_squares(ctx, G, m * n, d_f2);
+    else frob2_kernel<<<1, 256, 0, ctx->stream>>>(G, m, n, ldg, d_f2);
     ctx->ctr.launches++;
     double f2 = 0.0;
     TNR_CUDA(cudaMemcpyAsync(&f2, d_f2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -214,6 +299,74 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
     const double floor2 = f2 * 1e-34;
     const int max_sweeps = 40;
     int sweeps = 0;
+    // Tall matrices: precondition with the eigenvectors W of the Gram matrix G^T G (one DMMA
+    // GEMM + a small n x n Jacobi) and rotate G <- G W, V <- V W by GEMM.  G W already has
+    // nearly orthogonal columns, so the accurate one-sided sweeps below converge in 1-2 passes
+    // over the tall matrix instead of ~10; accuracy is that of Jacobi on G W (W is orthogonal).
+    if (!ctx->disable_precondition && m >= 4 * n && n >= 32 && ldg == m && (!V || ldv == n)) {
+        double* gram = dalloc(ctx, (size_t)n * n);
+        double* W = dalloc(ctx, (size_t)n * n);
+        gemm(ctx, 'T', 'N', (int)n, (int)n, (int)m, 1.0, G, ldg, G, ldg, 0.0, gram, n);
+        symmetrize(ctx, gram, n);
+        set_identity(ctx, W, n);
+        jacobi_orthogonalize(ctx, gram, n, n, n, W, n);
+        double* tmp = dalloc(ctx, (size_t)m * n);
+        gemm(ctx, 'N', 'N', (int)m, (int)n, (int)n, 1.0, G, ldg, W, n, 0.0, tmp, m);
+        TNR_CUDA(cudaMemcpyAsync(G, tmp, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        dfree(ctx, tmp);
+        if (V) {
+            double* tv = dalloc(ctx, (size_t)n * n);
+            gemm(ctx, 'N', 'N', (int)n, (int)n, (int)n, 1.0, V, ldv, W, n, 0.0, tv, n);
+            TNR_CUDA(cudaMemcpyAsync(V, tv, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     ctx->stream));
+            dfree(ctx, tv);
+        }
+        dfree(ctx, gram);
+        dfree(ctx, W);
+        ctx->ctr.preconditioned_jacobi++;
+    }
+    // block variant when a pair of column blocks (G and V columns) fits in shared memory
+    const long long rows = m + (V ? n : 0);
+    int BC = 0;
+    for (int cand : {16, 8, 4})
+        if (!BC && 2LL * cand * rows * 8 <= 200 * 1024 && n >= 2 * cand) BC = cand;
+    if (BC && !ctx->disable_block_jacobi) {
+        const int nblk = (int)((n + BC - 1) / BC);
+        const int nblk_pad = (nblk + 1) & ~1;
+        const size_t smem = (size_t)2 * BC * rows * 8;
+        auto launch = [&](int round) {
+            if (BC == 16) jacobi_block_round_kernel<16><<<nblk_pad / 2, 256, smem, ctx->stream>>>(
+                G, (int)m, (int)n, ldg, V, (int)n, ldv, round, nblk_pad, tol, floor2, d_rot);
+            else if (BC == 8) jacobi_block_round_kernel<8><<<nblk_pad / 2, 256, smem, ctx->stream>>>(
+                G, (int)m, (int)n, ldg, V, (int)n, ldv, round, nblk_pad, tol, floor2, d_rot);
+            else jacobi_block_round_kernel<4><<<nblk_pad / 2, 256, smem, ctx->stream>>>(
+                G, (int)m, (int)n, ldg, V, (int)n, ldv, round, nblk_pad, tol, floor2, d_rot);
+        };
+        static bool configured = false;
+        if (!configured) {
+            TNR_CUDA(cudaFuncSetAttribute(jacobi_block_round_kernel<16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            TNR_CUDA(cudaFuncSetAttribute(jacobi_block_round_kernel<8>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            TNR_CUDA(cudaFuncSetAttribute(jacobi_block_round_kernel<4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+        for (; sweeps < max_sweeps; ++sweeps) {
+            TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
+            for (int round = 0; round < nblk_pad - 1; ++round) launch(round);
+            ctx->ctr.launches += nblk_pad - 1;
+            TNR_CUDA(cudaGetLastError());
+            int rot = 0;
+            TNR_CUDA(cudaMemcpyAsync(&rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            TNR_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (rot == 0) { ++sweeps; break; }
+        }
+        TNR_CUDA(cudaFreeAsync(d_rot, ctx->stream));
+        dfree(ctx, d_f2);
+        return sweeps;
+    }
     for (; sweeps < max_sweeps; ++sweeps) {
         TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
         for (int round = 0; round < npad - 1; ++round) {

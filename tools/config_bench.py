@@ -13,6 +13,10 @@ cases = {
     "trg128": (lambda: tk.TRG(tk.classical_ising(tk.Trivial)), 128, 7, 2.0, tk.ising_βc, tk.f_onsager),
     "btrg128z2": (lambda: tk.BTRG(tk.classical_ising(tk.Z2Irrep)), 128, 7, 2.0, tk.ising_βc, tk.f_onsager),
     "trg128z3": (lambda: tk.TRG(tk.classical_potts(3)), 128, 7, 2.0, tk.potts_βc(3), -4.119552029995684),
+    "atrg3d16": (lambda: tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial)), 16, 4, 8.0, tk.ising_βc_3D, -3.507),
+    "atrg3d24": (lambda: tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial)), 24, 4, 8.0, tk.ising_βc_3D, -3.507),
+    "hotrg64z2": (lambda: tk.HOTRG(tk.classical_ising(tk.Z2Irrep)), 64, 7, 4.0, tk.ising_βc, tk.f_onsager),
+    "atrg64": (lambda: tk.ATRG(tk.classical_ising(tk.Trivial)), 64, 6, 4.0, tk.ising_βc, tk.f_onsager),
     "hotrg32": (lambda: tk.HOTRG(tk.classical_ising(tk.Trivial)), 32, 6, 4.0, tk.ising_βc, tk.f_onsager),
 }
 for name in which:
