@@ -476,3 +476,12 @@ def hotrg3d_chunk_contract(Qk, Pk):
     (hotrg3d.jl:116-120 after absorbing Ux into A1 and A2).  Used by bench.py's cpu_baseline
     leg as the bounded CPU sample of the workload."""
     return Qk.T @ Pk
+
+
+def finalize_two_by_two(scheme):
+    """src/utility/finalize.jl:17-25 (2x2 unit-cell norm)."""
+    T = scheme.T
+    n = abs(np.einsum("gaed,dbfg,cfbh,heac->", T, T, T, T, optimize=True))
+    f = n ** 0.25
+    scheme.T = T / f
+    return f

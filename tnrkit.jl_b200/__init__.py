@@ -11,7 +11,8 @@ from .models import (ChargedArray, Trivial, Z2Irrep, ZNIrrep, classical_ising, c
                      classical_potts, f_onsager, ising_bc, ising_bc_3D, ising_βc, ising_βc_3D,
                      potts_bc, potts_βc)
 from .schemes import (ATRG, ATRG_3D, BTRG, HOTRG, HOTRG_3D, TRG, Finalizer, TNRScheme,
-                      allgather_last_leg, beta_sweep, default_Finalizer, finalize, run, run_,
+                      allgather_last_leg, beta_sweep, default_Finalizer, finalize,
+                      finalize_two_by_two, run, run_, two_by_two_Finalizer,
                       shard_range)
 from .stopping import MultipleCrit, convcrit, maxiter, stopcrit, trivial_convcrit
 from .symmetric import Leg, SymTensor, sym_contract, sym_svd_trunc

@@ -385,3 +385,29 @@ def beta_sweep(scheme_cls, model, betas, trscheme, criterion, **scheme_kwargs):
     for g in gathered:
         merged.update(g)
     return [merged[i] for i in range(len(betas))]
+
+
+def finalize_two_by_two(scheme):
+    """finalize_two_by_two!(scheme::Union{TRG,ATRG,HOTRG}) -- src/utility/finalize.jl:17-25:
+    n = |T[7 1;5 4] T[4 2;6 7] T[3 6;2 8] T[8 5;1 3]|, T /= n^(1/4), returns n^(1/4).
+    Dense tensors only (block-sparse schemes are densified on the fly)."""
+    import ctypes as C_
+
+    from .tensor import contract as _contract
+
+    T = scheme.T
+    if getattr(scheme, "sym", False):
+        T = DeviceTensor.from_numpy(T.to_dense(), 2, scheme.ctx)
+    # labels: 7=g 1=a 5=e 4=d 2=b 6=f 3=c 8=h
+    X = _contract(T, "gaed", T, "dbfg", "aebf")      # sum over d, g
+    Y = _contract(T, "cfbh", T, "heac", "fbea")      # sum over c, h
+    n = abs(float(_contract(X, "aebf", Y, "fbea", "").to_numpy().reshape(-1)[0]))
+    f = n ** 0.25
+    if getattr(scheme, "sym", False):
+        scheme.T.scale(1.0 / f)
+    else:
+        scheme.ctx.call("tnr_scale", scheme.T.ptr, scheme.T.size, 1.0 / f)
+    return f
+
+
+two_by_two_Finalizer = Finalizer(finalize_two_by_two, float)
