@@ -54,10 +54,11 @@ def test_models_testset(tk, model, beta, answer):
 
 
 def test_3d_models_testset(tk):
-    # test/models.jl:80-86 style: 3D Ising, both symmetry variants, vs -3.508 (approximation)
+    # test/models.jl:25-28,80-86: HOTRG_3D, truncrank(8), maxiter(25), rtol 1e-3 vs -3.508 for the
+    # Trivial and the Z2 tensor
     for T in (tk.classical_ising_3D(tk.Trivial), tk.classical_ising_3D()):
-        data = tk.run(tk.HOTRG_3D(T), tk.truncrank(6), tk.maxiter(12), verbosity=0)
-        assert rel(tk.free_energy(data, tk.ising_βc_3D, scalefactor=8.0), -3.508) < 2.0e-3
+        data = tk.run(tk.HOTRG_3D(T), tk.truncrank(8), tk.maxiter(25), verbosity=0)
+        assert rel(tk.free_energy(data, tk.ising_βc_3D, scalefactor=8.0), -3.508) < 1.0e-3
 
 
 def test_two_by_two_finalizer(tk):
