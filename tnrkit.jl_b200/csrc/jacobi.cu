@@ -185,6 +185,18 @@ __global__ void __launch_bounds__(256) jacobi_block_round_kernel(
     }
 }
 
+// Convergence test of the one-sided iteration from the Gram matrix: counts the column pairs
+// that still violate |g_i . g_j| <= tol ||g_i|| ||g_j|| (same criterion as the sweeps).
+__global__ void gram_violations_kernel(const double* __restrict__ gram, int n, double tol,
+                                       double floor2, int* count) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * n) return;
+    int i = (int)(idx % n), j = (int)(idx / n);
+    if (i >= j) return;
+    double a = gram[(long long)i * n + i], b = gram[(long long)j * n + j], c = gram[(long long)j * n + i];
+    if (fabs(c) > tol * sqrt(a * b) && a > floor2 && b > floor2) atomicAdd(count, 1);
+}
+
 __global__ void __launch_bounds__(256) frob2_kernel(const double* __restrict__ G, long long m,
                                                     long long n, long long ldg, double* out) {
     __shared__ double red[256];
@@ -367,7 +379,25 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
         dfree(ctx, d_f2);
         return sweeps;
     }
+    // tall problems: a Gram GEMM (2 m n^2 flop on the tensor cores) is far cheaper than a sweep
+    // (n-1 passes over the m x n matrix), so convergence is tested on the Gram matrix before
+    // every sweep -- a preconditioned problem usually needs zero or one sweep.
+    const bool gram_check = !ctx->disable_precondition && m >= 4 * n && n >= 32 && ldg == m;
     for (; sweeps < max_sweeps; ++sweeps) {
+        if (gram_check) {
+            double* gram = dalloc(ctx, (size_t)n * n);
+            gemm(ctx, 'T', 'N', (int)n, (int)n, (int)m, 1.0, G, ldg, G, ldg, 0.0, gram, n);
+            TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
+            long long nn = n * n;
+            gram_violations_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(
+                gram, (int)n, tol, floor2, d_rot);
+            ctx->ctr.launches++;
+            int viol = 0;
+            TNR_CUDA(cudaMemcpyAsync(&viol, d_rot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            TNR_CUDA(cudaStreamSynchronize(ctx->stream));
+            dfree(ctx, gram);
+            if (viol == 0) break;
+        }
         TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
         for (int round = 0; round < npad - 1; ++round) {
             if (m > 2048)
