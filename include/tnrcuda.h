@@ -167,6 +167,15 @@ int tnr_hotrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int
  * the full-size buffer; the permute of step! is NOT applied (call tnr_permute). */
 int tnr_hotrg3d_substep(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
                         double* Tout, int64_t* dims_out, int64_t f_begin, int64_t f_end);
+/* Same z-compression, with the all-gather fused into the producing kernel: `Tout_peers[r]` is
+ * rank r's full-size T' buffer as a peer-mapped device pointer (NVLink / NVSwitch; e.g. from
+ * torch symmetric memory or cudaIpcOpenMemHandle), `self` this rank's index.  Every chi^4 slab
+ * T'[:, :, :, d, :, f] is stored to ALL buffers by the kernel that produces it, so the transfer
+ * overlaps the chunk loop and no collective follows; the caller only needs a cross-rank barrier
+ * before reading its buffer. */
+int tnr_hotrg3d_substep_peers(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                              double* const* Tout_peers, int npeers, int self, int64_t* dims_out,
+                              int64_t f_begin, int64_t f_end);
 /* step!(::ATRG_3D, trunc)           src/schemes/atrg3d.jl:85-97 */
 int tnr_atrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
                     int64_t* dims_out);

@@ -31,10 +31,21 @@ def _worker(rank, world, port, chi, nsteps, q):
                             device_id=torch.device("cuda", rank))
     import tnrkit.jl_b200 as tk
 
-    s = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial))
-    assert s.shard
-    data = tk.run(s, tk.truncrank(chi), tk.maxiter(nsteps), verbosity=0)
-    q.put((rank, data))
+    import ctypes as C
+
+    ctx = tk.default_context()
+    out = {}
+    for mode in ("peers", "nccl"):
+        s = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial),
+                        peer_scatter=None if mode == "peers" else False)
+        assert s.shard
+        v0 = C.c_double()
+        ctx.call("tnr_get_counter", b"peer_scatter_launches", C.byref(v0))
+        out[mode] = tk.run(s, tk.truncrank(chi), tk.maxiter(nsteps), verbosity=0)
+        v1 = C.c_double()
+        ctx.call("tnr_get_counter", b"peer_scatter_launches", C.byref(v1))
+        out[mode + "_peer_launches"] = v1.value - v0.value
+    q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,6 +72,12 @@ def test_hotrg3d_sharded_two_gpus():
         assert p.exitcode == 0
     ref = np.array(o.run(o.HOTRG_3D(o.classical_ising_3D()), chi, nsteps))
     for r in range(2):
-        got = np.array(res[r])
-        assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-10
-    assert res[0] == res[1]  # replicas stay bit-identical
+        for mode in ("peers", "nccl"):
+            got = np.array(res[r][mode])
+            assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-10, (r, mode)
+        assert res[r]["nccl_peer_launches"] == 0
+        # the two exchange mechanisms move the same numbers: bit-identical norm lists
+        assert res[r]["peers"] == res[r]["nccl"]
+    assert res[0]["nccl"] == res[1]["nccl"]  # replicas stay bit-identical
+    print("peer-scatter launches per rank:", res[0]["peers_peer_launches"],
+          "(0 means symmetric memory was unavailable and the NCCL path was used)")

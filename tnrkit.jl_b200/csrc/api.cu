@@ -421,7 +421,25 @@ int tnr_hotrg3d_substep(tnr_context* ctx, const double* T, const int64_t* dims, 
         Dims od = hotrg3d_substep_dims(t.d, chi);
         TNR_CHECK(0 <= f_begin && f_begin <= f_end && f_end <= od[5], "substep: bad slice range");
         DT out = DT::view(c, Tout, od);
-        hotrg3d_substep(c, t, chi, out, f_begin, f_end);
+        hotrg3d_substep(c, t, chi, out, f_begin, f_end, nullptr, 0);
+        if (dims_out)
+            for (int i = 0; i < 6; ++i) dims_out[i] = od[i];
+    });
+}
+
+int tnr_hotrg3d_substep_peers(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                              double* const* Tout_peers, int npeers, int self, int64_t* dims_out,
+                              int64_t f_begin, int64_t f_end) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        Context* c = &ctx->c;
+        TNR_CHECK(Tout_peers && npeers >= 1 && npeers <= 16 && self >= 0 && self < npeers,
+                  "substep_peers: bad peer table");
+        DT t = in_view(c, T, to_dims(dims, 6));
+        Dims od = hotrg3d_substep_dims(t.d, chi);
+        TNR_CHECK(0 <= f_begin && f_begin <= f_end && f_end <= od[5], "substep: bad slice range");
+        DT out = DT::view(c, Tout_peers[self], od);
+        hotrg3d_substep(c, t, chi, out, f_begin, f_end, Tout_peers, npeers);
         if (dims_out)
             for (int i = 0; i < 6; ++i) dims_out[i] = od[i];
     });
@@ -556,6 +574,7 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "gemm_launches") *value = (double)c.gemm_launches;
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "peer_scatter_launches") *value = (double)c.peer_scatter_launches;
         else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;

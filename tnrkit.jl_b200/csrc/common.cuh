@@ -35,6 +35,7 @@ struct Counters {
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
     unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
+    unsigned long long peer_scatter_launches = 0;  // slab scatters that also stored to peer GPUs
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
@@ -100,6 +101,8 @@ bool gemm_tma_tn(Context* ctx, int m, int n, int k, double alpha, const double* 
 // dst[sum i_j*dstride_j] = src[sum i_j*sstride_j] for all multi-indices i < dims.
 void strided_copy(Context* ctx, const double* src, double* dst, int rank,
                   const long long* dims, const long long* sstride, const long long* dstride);
+void strided_copy_multi(Context* ctx, const double* src, double* const* dsts, int ndst, int rank,
+                        const long long* dims, const long long* sstride, const long long* dstride);
 // dst (compact, column major, dims[perm[k]]) leg k = src leg perm[k]
 void permute(Context* ctx, const double* src, double* dst, int rank, const long long* dims,
              const int* perm);

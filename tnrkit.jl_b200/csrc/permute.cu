@@ -122,6 +122,37 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const double* __restrict
     dst[doff] = src[soff];
 }
 
+// Same as copy_rows_kernel but every element is stored to `ndst` destinations with identical
+// layout: the local buffer and the peer-mapped buffers of the other GPUs (NVLink stores).  Used
+// by the sharded HOTRG_3D step to publish each T' slab to all ranks from the kernel that
+// produces it (no separate all-gather).
+constexpr int MAXDST = 16;
+struct DstTable {
+    double* p[MAXDST];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) copy_rows_multi_kernel(const double* __restrict__ src,
+                                                              const DstTable dsts,
+                                                              const CopyParams p) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= p.total) return;
+    long long i = idx % p.ni;
+    long long rest = idx / p.ni;
+    long long soff = i * p.si_s, doff = i * p.si_d;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+        if (d < p.rank) {
+            long long k = rest % p.dims[d];
+            rest /= p.dims[d];
+            soff += k * p.ss[d];
+            doff += k * p.ds[d];
+        }
+    }
+    const double v = src[soff];
+    for (int t = 0; t < dsts.n; ++t) dsts.p[t][doff] = v;
+}
+
 // contiguous copy, 16-byte vectorised
 __global__ void __launch_bounds__(256) copy_flat_kernel(const double* __restrict__ src,
                                                         double* __restrict__ dst, long long n,
@@ -238,6 +269,34 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
     }
     TNR_CUDA(cudaGetLastError());
     ctx->ctr.launches++;
+}
+
+// dst_k[i.dstride] = src[i.sstride] for every destination k (element-wise kernel; used for the
+// small chi^4 slabs of the sharded HOTRG_3D step, where the destinations are peer GPUs)
+void strided_copy_multi(Context* ctx, const double* src, double* const* dsts, int ndst, int rank,
+                        const long long* dims, const long long* sstride,
+                        const long long* dstride) {
+    TNR_CHECK(ndst >= 1 && ndst <= MAXDST, "strided_copy_multi: 1..16 destinations");
+    TNR_CHECK(rank >= 1 && rank <= MAXR + 1, "strided_copy_multi: rank out of range");
+    CopyParams p{};
+    long long total = 1;
+    p.ni = dims[0]; p.si_s = sstride[0]; p.si_d = dstride[0];
+    p.rank = 0;
+    for (int i = 0; i < rank; ++i) total *= dims[i];
+    for (int i = 1; i < rank; ++i) {
+        p.dims[p.rank] = dims[i]; p.ss[p.rank] = sstride[i]; p.ds[p.rank] = dstride[i];
+        p.rank++;
+    }
+    if (total == 0) return;
+    p.total = total;
+    DstTable t{};
+    t.n = ndst;
+    for (int k = 0; k < ndst; ++k) t.p[k] = dsts[k];
+    copy_rows_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, t, p);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+    ctx->ctr.peer_scatter_launches += (ndst > 1);
+    ctx->ctr.permute_bytes += 8.0 * (double)total * (1 + ndst);
 }
 
 void permute(Context* ctx, const double* src, double* dst, int rank, const long long* dims,

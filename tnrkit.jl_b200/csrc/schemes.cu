@@ -258,7 +258,8 @@ Dims hotrg3d_substep_dims(const Dims& d, int chi) {
 }
 
 // One z-compression (hotrg3d.jl:124-129) writing T_out[..., f] for f in [f0, f1).
-void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0, long long f1) {
+void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0, long long f1,
+                     double* const* peers, int npeers) {
     TNR_CHECK(T.rank() == 6, "hotrg3d: rank-6 tensor expected");
     TNR_CHECK(T.d[0] == T.d[1] && T.d[2] == T.d[4] && T.d[3] == T.d[5], "hotrg3d: leg dims");
     Dims od = hotrg3d_substep_dims(T.d, chi);
@@ -311,7 +312,15 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
             long long wd[4] = {Dz, ny, Dz, ny};
             long long ws[4] = {1, Dz, Dz * ny, Dz * ny * Dz};
             long long wdst[4] = {so[0], so[4], so[1], so[2]};
-            strided_copy(ctx, W.p, Tout.p + d * so[3] + f * so[5], 4, wd, ws, wdst);
+            const long long off = d * so[3] + f * so[5];
+            if (npeers > 1) {
+                // publish the slab to every rank's T' buffer (peer-mapped, NVLink stores)
+                double* dst[16];
+                for (int r = 0; r < npeers; ++r) dst[r] = peers[r] + off;
+                strided_copy_multi(ctx, W.p, dst, npeers, 4, wd, ws, wdst);
+            } else {
+                strided_copy(ctx, W.p, Tout.p + off, 4, wd, ws, wdst);
+            }
         }
     }
 }
@@ -321,7 +330,7 @@ DT hotrg3d_step(Context* ctx, const DT& T0, int chi) {
     DT T = clone(T0);
     for (int it = 0; it < 3; ++it) {
         DT Tn(ctx, hotrg3d_substep_dims(T.d, chi));
-        hotrg3d_substep(ctx, T, chi, Tn, 0, Tn.d[5]);
+        hotrg3d_substep(ctx, T, chi, Tn, 0, Tn.d[5], nullptr, 0);
         T = permute(Tn, {5, 3, 1, 2, 0, 4});  // ((6,4),(2,3,1,5))
     }
     return T;

@@ -14,7 +14,10 @@ DT hotrg_step(Context* ctx, const DT& T, int chi);
 DT atrg_step(Context* ctx, const DT& T, int chi);
 
 Dims hotrg3d_substep_dims(const Dims& d, int chi);
-void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0, long long f1);
+// peers != nullptr: the T' buffers of all `npeers` ranks (own buffer included, peer-mapped
+// device pointers); every slab is stored to all of them by the producing kernel
+void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0, long long f1,
+                     double* const* peers, int npeers);
 DT hotrg3d_step(Context* ctx, const DT& T, int chi);
 DT atrg3d_step(Context* ctx, const DT& T, int chi);
 

@@ -280,7 +280,7 @@ class HOTRG_3D(TNRScheme):
     _step_fn = "tnr_hotrg3d_step"
     PERM = (5, 3, 1, 2, 0, 4)  # ((6,4),(2,3,1,5))
 
-    def __init__(self, T, ctx=None, shard=None, group=None):
+    def __init__(self, T, ctx=None, shard=None, group=None, peer_scatter=None):
         super().__init__(T, ctx)
         self.group = group
         if shard is None:
@@ -292,6 +292,30 @@ class HOTRG_3D(TNRScheme):
             except Exception:
                 shard = False
         self.shard = bool(shard)
+        # peer_scatter: publish every T' slab to all ranks with NVLink stores from the producing
+        # kernel (torch symmetric memory provides the peer-mapped buffers) instead of an NCCL
+        # all-gather afterwards.  None = try, fall back to NCCL when symmetric memory is absent.
+        self.peer_scatter = peer_scatter
+        self._symm = None      # (buffers, handles) of the two ping-pong symmetric T' buffers
+        self._symm_turn = 0
+
+    def _symm_buffers(self, nelem):
+        """Two symmetric-memory buffers of at least nelem doubles (allocated once, collectively)."""
+        import torch
+        import torch.distributed as dist
+
+        if self._symm is not None and self._symm[0][0].numel() >= nelem:
+            return self._symm
+        import torch.distributed._symmetric_memory as symm_mem
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        bufs, hdls = [], []
+        for _ in range(2):
+            t = symm_mem.empty(nelem, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+            hdls.append(symm_mem.rendezvous(t, group=grp))
+            bufs.append(t)
+        self._symm = (bufs, hdls)
+        return self._symm
 
     def _substep(self, chi):
         import torch.distributed as dist
@@ -299,13 +323,36 @@ class HOTRG_3D(TNRScheme):
         d = self.T.dims
         od = (d[0], d[1], min(chi, d[4] * d[4]), min(chi, d[5] * d[5]),
               min(chi, d[4] * d[4]), min(chi, d[5] * d[5]))
-        out = DeviceTensor.empty(od, 2, self.ctx)
         if self.shard:
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         else:
             world, rank = 1, 0
         lo, hi = shard_range(od[5], rank, world)
         dims_out = (C.c_int64 * 6)()
+        nelem = math.prod(od)
+        use_peers = world > 1 and self.peer_scatter is not False
+        if use_peers:
+            try:
+                # size the symmetric buffers for the saturated tensor so they are allocated once
+                bufs, hdls = self._symm_buffers(max(nelem, chi ** 6))
+            except Exception as e:  # symmetric memory unavailable on this platform
+                if self.peer_scatter:
+                    raise
+                log.warning("symmetric memory unavailable (%s); using the NCCL all-gather", e)
+                self.peer_scatter = False
+                use_peers = False
+        if use_peers:
+            turn = self._symm_turn
+            self._symm_turn ^= 1
+            buf, hdl = bufs[turn], hdls[turn]
+            ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            self.ctx.call("tnr_hotrg3d_substep_peers", self.T.ptr, _lib.i64(d), chi, ptrs, world,
+                          rank, dims_out, lo, hi)
+            hdl.barrier()  # all ranks' peer stores have landed in this buffer
+            out = DeviceTensor(buf, od, 2, self.ctx)
+            self.T = out.permute(self.PERM)
+            return
+        out = DeviceTensor.empty(od, 2, self.ctx)
         self.ctx.call("tnr_hotrg3d_substep", self.T.ptr, _lib.i64(d), chi, out.ptr, dims_out,
                       lo, hi)
         if world > 1:
