@@ -107,3 +107,40 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "tnr_oracle" not in src and "import oracle" not in src, f
+
+
+def test_symmetric_sector_bookkeeping(tk):
+    """Host-side structure of block-sparse Z_N tensors (no device needed): allowed charge
+    tuples, coupled-sector row/column offsets."""
+    L = lambda s: tk.Leg({0: 2, 1: 3, 2: 1}, s)
+    t = tk.SymTensor(3, [L(+1), L(+1), L(-1), L(-1)], {})
+    keys = list(t.keys())
+    assert len(keys) == 27 and all((a + b - c - d) % 3 == 0 for a, b, c, d in keys)
+    assert t.dims == (6, 6, 6, 6)
+    assert t.block_dims((0, 1, 1, 0)) == (2, 3, 3, 2)
+    rows = t._tuples([0, 1], negate=False)
+    cols = t._tuples([2, 3], negate=True)
+    assert sorted(rows) == sorted(cols) == [0, 1, 2]
+    for c in (0, 1, 2):
+        # offsets are cumulative sizes; rows and columns of a coupled sector have equal totals
+        # here because both pairs of legs carry the same spaces
+        tot_r = rows[c][-1][1] + rows[c][-1][2]
+        tot_c = cols[c][-1][1] + cols[c][-1][2]
+        assert tot_r == tot_c == sum(t.legs[0].dims[a] * t.legs[1].dims[b]
+                                     for a in range(3) for b in range(3) if (a + b) % 3 == c)
+        off = 0
+        for key, o_, size in rows[c]:
+            assert o_ == off and sum(key) % 3 == c
+            off += size
+    leg = tk.Leg({2: 1, 0: 4}, -1)
+    assert leg.charges == (0, 2) and leg.offsets == {0: 0, 2: 4} and leg.total == 5
+    assert leg.flipped().sign == +1 and leg.same_space(leg.flipped())
+
+
+def test_charged_model_arrays(tk):
+    t = tk.classical_ising()
+    assert isinstance(t, tk.ChargedArray) and t.N == 2 and t.signs == (1, 1, -1, -1)
+    p = tk.classical_potts(3)
+    assert p.N == 3 and p.charges[0] == (0, 1, 2)
+    assert type(np.asarray(p)) is np.ndarray
+    assert getattr(tk.classical_ising(tk.Trivial), "charges", None) is None

@@ -68,7 +68,14 @@ class SymTensor:
         self.N = int(N)
         self.legs = list(legs)
         self.blocks = dict(blocks)
-        self.ctx = ctx or _lib.default_context()
+        self._ctx = ctx
+
+    @property
+    def ctx(self):
+        # resolved lazily so that the sector bookkeeping can be used (and tested) without a GPU
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
 
     # ---- structure ---------------------------------------------------------
     def allowed(self, key):
@@ -120,7 +127,7 @@ class SymTensor:
     def permute(self, perm):
         legs = [self.legs[p] for p in perm]
         blocks = {tuple(k[p] for p in perm): b.permute(perm) for k, b in self.blocks.items()}
-        return SymTensor(self.N, legs, blocks, self.ctx)
+        return SymTensor(self.N, legs, blocks, self._ctx)
 
     # ---- coupled-sector matrices ----------------------------------------------
     def _tuples(self, which, negate):
