@@ -267,6 +267,10 @@ def run_gpu(args):
     gemm_ms, gemm_fl, gemm_n = ctx.gemm_timing_read()
     ctx.gemm_timing(False)
     ctr = ctx.counters()
+    import ctypes as _C
+    _v = _C.c_double()
+    ctx.call("tnr_get_counter", b"peer_scatter_launches", _C.byref(_v))
+    peer_launches = int(_v.value)
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,7 +294,10 @@ def run_gpu(args):
                             f"timed steps are RG iterations {args.warmup + 1}.."
                             f"{args.warmup + K} of run! (legs {scheme.T.dims})",
                 "parallelism": "1 GPU" if world == 1 else
-                f"open x-bond sharded over {world} GPUs, 1 NCCL all-gather per z-compression",
+                f"open x-bond sharded over {world} GPUs; exchange: " +
+                ("every T' slab stored to all ranks over NVLink by the kernel that produces it "
+                 f"({peer_launches} fused scatter launches, symmetric memory), no collective"
+                 if peer_launches else "1 NCCL all-gather per z-compression"),
                 "l2": "inputs (chi^6 doubles = %.2f GB) exceed L2; no flush needed" %
                       (scheme.T.size * 8 / 1e9),
                 "steps_per_s": 1.0 / sec,
