@@ -12,7 +12,9 @@ real `classical_ising_3D(Trivial, beta_c)` tensor, so the W warm-up steps are RG
 timed steps are steady-state chi^6 tensors.  Synthetic data: the model tensor is analytic.
 
 N > 1 (torchrun, one process per GPU, NCCL): the chi^11 contraction of every z-compression is
-sharded along the new open x-bond, one all-gather per z-compression (strong scaling).
+sharded along the new open x-bond (strong scaling).  T' is replicated either by NVLink peer stores
+fused into the slab-producing kernel (torch symmetric memory) or by one NCCL all-gather per
+z-compression; the JSON line says which.
 
 Timing: CUDA events on the engine stream, barrier + synchronize on both sides, max over
 ranks.  Inputs (1.5 GB at chi=24) exceed the 126 MB L2, so no explicit flush is needed.
