@@ -51,7 +51,9 @@ int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
 /* any counter by name: "launches", "gemm_launches", "grouped_gemm_launches",
  * "tma_gemm_launches", "gemm_flops", "permute_bytes" */
 int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
-/* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests) */
+/* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests);
+ * "disable_subspace", "disable_block_jacobi", "disable_precondition" switch the fast SVD/eigh
+ * paths off; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
  * library stream; read returns the summed milliseconds, flops and the launch count. */
@@ -75,6 +77,13 @@ int tnr_gemm_strided_batched(tnr_context* ctx, char transa, char transb, int m, 
                              double alpha, const double* A, int64_t lda, int64_t strideA,
                              const double* B, int64_t ldb, int64_t strideB, double beta,
                              double* C, int64_t ldc, int64_t strideC, int batch);
+/* C(m x n) = A^T B with A: k x m, B: k x n (column major; the 'T','N' case of tnr_gemm, alpha = 1,
+ * beta = 0) computed on the INT8 tensor cores by error-free splitting (Ozaki scheme, tcgen05 +
+ * TMEM): FP64-level accuracy relative to (row max) x (column max), ~2x the DMMA rate.  Opt-in:
+ * tnr_set_option(ctx, "ozaki", 8) selects 8 digit planes (36 exact INT8 products) and also routes
+ * the chi^3 x chi^3 x chi^3 chunk contraction of tnr_hotrg3d_step / _substep through it. */
+int tnr_gemm_ozaki(tnr_context* ctx, int m, int n, int k, const double* A, int64_t lda,
+                   const double* B, int64_t ldb, double* C, int64_t ldc);
 /* Grouped GEMM: `count` independent problems C_g = alpha op(A_g) op(B_g) + beta C_g in ONE
  * launch -- the per-coupled-sector block products of a Z2 / ZN / U1 block-sparse contraction
  * (TensorKit `mul!` loops over `blocks(t)`; e.g. the per-sector products behind every

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "tnr_gemm_strided_batched": [C.c_void_p, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int,
                                  C.c_double, _c_dp, C.c_int64, C.c_int64, _c_dp, C.c_int64,
                                  C.c_int64, C.c_double, _c_dp, C.c_int64, C.c_int64, C.c_int],
+    "tnr_gemm_ozaki": [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_dp, C.c_int64, _c_dp, C.c_int64,
+                       _c_dp, C.c_int64],
     "tnr_gemm_grouped": [C.c_void_p, C.c_char, C.c_char, C.c_int, C.POINTER(GemmProblem),
                          C.c_double, C.c_double],
     "tnr_permute": [C.c_void_p, _c_dp, _c_dp, C.c_int, _c_i64p, C.POINTER(C.c_int)],

@@ -137,6 +137,10 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return 1;
     return guard(ctx, [&] {
         if (std::strcmp(key, "disable_tma") == 0) ctx->c.disable_tma = value != 0;
+        else if (std::strcmp(key, "ozaki") == 0) {
+            TNR_CHECK(value == 0 || (value >= 4 && value <= 10), "ozaki: 0 (off) or 4..10 digit planes");
+            ctx->c.ozaki_slices = (int)value;
+        }
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
@@ -242,6 +246,22 @@ int tnr_gemm_grouped(tnr_context* ctx, char transa, char transb, int count,
             v[g] = GroupedProblem{q.m, q.n, q.k, q.A, q.lda, q.B, q.ldb, q.C, q.ldc};
         }
         gemm_grouped(&ctx->c, transa, transb, v, alpha, beta);
+    });
+}
+
+int tnr_gemm_ozaki(tnr_context* ctx, int m, int n, int k, const double* A, int64_t lda,
+                   const double* B, int64_t ldb, double* C, int64_t ldc) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        Context* c = &ctx->c;
+        TNR_CHECK(c->ozaki_slices > 0, "gemm_ozaki: enable with tnr_set_option(ctx, \"ozaki\", 8)");
+        TNR_CHECK(ozaki_applicable(c, m, n, k),
+                  "gemm_ozaki: needs m, n, k >= 512, k % 16 == 0 and slices * k * 4096 < 2^31");
+        OzakiOperand a = ozaki_split(c, A, lda, m, k);
+        OzakiOperand b = ozaki_split(c, B, ldb, n, k);
+        ozaki_multiply(c, a, b, C, ldc);
+        ozaki_free(c, a);
+        ozaki_free(c, b);
     });
 }
 
@@ -574,6 +594,8 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "gemm_launches") *value = (double)c.gemm_launches;
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "ozaki_launches") *value = (double)c.ozaki_launches;
+        else if (n == "ozaki_gemms") *value = (double)c.ozaki_gemms;
         else if (n == "peer_scatter_launches") *value = (double)c.peer_scatter_launches;
         else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;

@@ -35,6 +35,8 @@ struct Counters {
     unsigned long long gemm_launches = 0;  // DMMA GEMM kernels
     unsigned long long grouped_gemm_launches = 0;  // of which grouped (per-sector) launches
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
+    unsigned long long ozaki_launches = 0;   // INT8 tcgen05 group kernels
+    unsigned long long ozaki_gemms = 0;      // FP64-equivalent GEMMs served by the Ozaki engine
     unsigned long long peer_scatter_launches = 0;  // slab scatters that also stored to peer GPUs
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
@@ -55,6 +57,7 @@ struct Context {
     bool disable_tma = false;  // force the cp.async GEMM (A/B testing)
     bool disable_subspace = false;  // force full Jacobi in eigh_trunc
     bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
+    int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
@@ -96,6 +99,19 @@ void gemm_grouped(Context* ctx, char transa, char transb, const std::vector<Grou
 // when the problem does not fit (caller falls back to the cp.async kernel)
 bool gemm_tma_tn(Context* ctx, int m, int n, int k, double alpha, const double* A, long long lda,
                  const double* B, long long ldb, double beta, double* C, long long ldc);
+
+// gemm_ozaki.cu: FP64-accurate TN GEMM on the INT8 tensor cores (tcgen05 + TMEM), opt-in
+struct OzakiOperand {        // int8 digit planes of the rows of a K-major FP64 matrix
+    int8_t* planes = nullptr;  // [slices][rows][K]
+    double* scale = nullptr;   // [rows] power-of-two row scale
+    long long rows = 0, K = 0;
+    int slices = 0;
+};
+bool ozaki_applicable(const Context* ctx, long long m, long long n, long long k);
+OzakiOperand ozaki_split(Context* ctx, const double* X, long long ld, long long rows, long long K);
+void ozaki_free(Context* ctx, OzakiOperand& o);
+void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, double* C,
+                    long long ldc);
 
 // ---- kernels: permute.cu ----
 // dst[sum i_j*dstride_j] = src[sum i_j*sstride_j] for all multi-indices i < dims.

@@ -1,0 +1,350 @@
+// FP64-accurate GEMM on the INT8 tensor cores (Ozaki scheme) -- opt-in engine for the
+// dominant TN contraction  C(m x n) = A^T B,  A: K x M, B: K x N, column major
+// (the (f,d)-chunk GEMM of HOTRG_3D, /root/reference/src/schemes/hotrg3d.jl:116-120).
+//
+// The FP64 tensor pipe (DMMA) tops out at ~36 TFLOP/s and the chunk GEMM already runs at 98 % of
+// that; the INT8 path of the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators
+// in TMEM) delivers ~2.3 POPS with this kernel.  Error-free splitting turns one FP64 product into
+// S(S+1)/2 exact INT8 products:
+//
+//   * every row x of A^T (and of B^T) is scaled by a power of two, |y| = |x| 2^-e < 1, and
+//     expanded in signed base-128 digits  y = sum_i q_i 2^(-6-7i),  |q_i| <= 64  (exact in FP64);
+//   * digit planes are multiplied exactly in INT8 x INT8 -> INT32 (K * 64^2 * S < 2^31);
+//     all pairs with i + j = t share one TMEM accumulator (the planes are simply concatenated
+//     along K), so there are S accumulation groups t = 0..S-1 with weight 2^(-12-7t);
+//   * groups are summed into C in FP64 from the smallest weight to the largest, scaled by
+//     2^(e_row + e_col).
+//
+// With S = 8 the neglected pairs (i + j >= 8) are below 9 * 2^-56 ~ 1.3e-16 per term relative
+// to (row max) x (column max): the truncation error is of the size of DGEMM's own rounding.
+//
+// Kernel structure: one TMA producer thread (3-D tensor maps: K x rows x plane, 128-byte
+// swizzle), one MMA thread issuing tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 256, K = 32)
+// into a 128 x 256 INT32 accumulator in TMEM, four epilogue warps (tcgen05.ld 32x32b) that
+// convert, scale and accumulate into the FP64 result.
+#include <cuda.h>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace tnr {
+namespace {
+
+constexpr int OBM = 128, OBN = 256, OBK = 128, OSTAGES = 4;
+constexpr int OA_BYTES = OBM * OBK, OB_BYTES = OBN * OBK, OSTAGE_BYTES = OA_BYTES + OB_BYTES;
+constexpr int OTHREADS = 192;
+constexpr int OTMEM_COLS = 256;
+constexpr size_t OSMEM = 1024 + (size_t)OSTAGES * OSTAGE_BYTES + 128;
+
+__device__ __forceinline__ unsigned o_smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void o_mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void o_mbar_expect_tx(unsigned bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// bounded wait: a protocol error becomes a trap (reported as a CUDA error), never a hang
+__device__ __forceinline__ void o_mbar_wait(unsigned bar, int parity) {
+    for (long long it = 0; it < (1LL << 30); ++it) {
+        unsigned ok;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;\n");
+}
+__device__ __forceinline__ void o_tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1,
+                                              int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, LBO = 16 B, SBO = 1024 B, version 1
+__device__ __forceinline__ uint64_t o_make_desc(unsigned smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void o_umma_i8(unsigned tmem_c, uint64_t adesc, uint64_t bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_c),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void o_umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
+                 : "memory");
+}
+
+struct OzakiParams {
+    double* C;
+    long long ldc;
+    const double* scaleA;  // 2^e per row of A^T
+    const double* scaleB;  // 2^e per row of B^T
+    int M, N, K;
+    int t;         // accumulation group: pairs (i, t - i), i = 0..t
+    double weight; // 2^(-12 - 7 t)
+    int accumulate;  // 0: C = value, 1: C += value
+};
+
+__global__ void __launch_bounds__(OTHREADS, 1)
+ozaki_group_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const OzakiParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned long long* bars = (unsigned long long*)(smem + (size_t)OSTAGES * OSTAGE_BYTES);
+    const unsigned full0 = o_smem_u32(bars), empty0 = o_smem_u32(bars + OSTAGES);
+    const unsigned tmem_full = o_smem_u32(bars + 2 * OSTAGES);
+    unsigned* tmem_ptr = (unsigned*)(bars + 2 * OSTAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * OBM, n0 = blockIdx.y * OBN;
+    const int KB = (p.K + OBK - 1) / OBK;
+    const int total = KB * (p.t + 1);  // k-blocks over all plane pairs of this group
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OSTAGES; ++s) {
+            o_mbar_init(full0 + 8 * s, 1);
+            o_mbar_init(empty0 + 8 * s, 1);
+        }
+        o_mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         o_smem_u32(tmem_ptr)),
+                     "n"(OTMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int i = 0; i <= p.t; ++i) {
+                const int j = p.t - i;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
+                    o_mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    unsigned full = full0 + 8 * s;
+                    o_mbar_expect_tx(full, OSTAGE_BYTES);
+                    unsigned dst = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
+                    o_tma_load_3d(dst, &mapA, kb * OBK, m0, i, full);
+                    o_tma_load_3d(dst + OA_BYTES, &mapB, kb * OBK, n0, j, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D = S32, A = B = signed int8, both K-major, N = 256, M = 128
+            const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) |
+                                   ((unsigned)(OBN >> 3) << 17) | ((unsigned)(OBM >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
+                o_mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                unsigned a_base = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
+                unsigned b_base = a_base + OA_BYTES;
+#pragma unroll
+                for (int k = 0; k < OBK / 32; ++k)
+                    o_umma_i8(tmem_base, o_make_desc(a_base + k * 32), o_make_desc(b_base + k * 32),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
+                o_umma_commit(empty0 + 8 * s);
+            }
+            o_umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        o_mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+        const double sa = (row < p.M) ? p.scaleA[row] * p.weight : 0.0;
+        for (int c0 = 0; c0 < OBN; c0 += 16) {
+            unsigned v[16];
+            unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                  "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                  "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    int col = n0 + c0 + j;
+                    if (col < p.N) {
+                        double val = (double)(int)v[j] * (sa * p.scaleB[col]);
+                        double* cp = p.C + (long long)col * p.ldc + row;
+                        *cp = p.accumulate ? (*cp + val) : val;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                     "n"(OTMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- error-free splitting of the rows of a K-major FP64 matrix into int8 digit planes ----
+// X: K x R column major (row r of X^T = contiguous column r, leading dimension ld).
+// planes[i][r][k] (int8, k contiguous), scale[r] = 2^e with |x| 2^-e < 1.
+__global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ X,
+                                                          long long ld, int K, int slices,
+                                                          int8_t* __restrict__ planes,
+                                                          long long plane_stride,
+                                                          double* __restrict__ scale) {
+    const int r = blockIdx.x;
+    const double* x = X + (long long)r * ld;
+    __shared__ double red[256];
+    double amax = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) amax = fmax(amax, fabs(x[k]));
+    red[threadIdx.x] = amax;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    amax = red[0];
+    int e = 0;
+    if (amax > 0.0 && isfinite(amax)) e = ilogb(amax) + 1;  // amax * 2^-e in [0.5, 1)
+    if (threadIdx.x == 0) scale[r] = ldexp(1.0, e);
+    int8_t* out = planes + (long long)r * K;
+    for (int k = threadIdx.x; k < K; k += 256) {
+        double y = ldexp(x[k], 6 - e);  // |y| < 64
+        double q = rint(y);
+        out[k] = (int8_t)(int)q;
+        double rem = y - q;             // |rem| <= 0.5, exact
+        for (int i = 1; i < slices; ++i) {
+            rem *= 128.0;
+            q = rint(rem);
+            out[(long long)i * plane_stride + k] = (int8_t)(int)q;
+            rem -= q;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn ozaki_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool make_plane_map(CUtensorMap* map, const int8_t* base, long long rows, long long K, int slices,
+                    int box_rows) {
+    EncodeTiledFn enc = ozaki_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)slices};
+    cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)OBK, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool ozaki_applicable(const Context* ctx, long long m, long long n, long long k) {
+    // exact int32 accumulation needs (slices) * K * 64^2 < 2^31; TMA needs 16-byte row strides
+    return ctx->ozaki_slices >= 2 && (k % 16) == 0 && m >= 512 && n >= 512 && k >= 512 &&
+           (double)ctx->ozaki_slices * (double)k * 4096.0 < 2147483648.0;
+}
+
+OzakiOperand ozaki_split(Context* ctx, const double* X, long long ld, long long rows, long long K) {
+    OzakiOperand o;
+    o.rows = rows;
+    o.K = K;
+    o.slices = ctx->ozaki_slices;
+    TNR_CUDA(cudaMallocAsync((void**)&o.planes, (size_t)o.slices * rows * K, ctx->stream));
+    o.scale = dalloc(ctx, rows);
+    ozaki_split_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(X, ld, (int)K, o.slices, o.planes,
+                                                               rows * K, o.scale);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+    return o;
+}
+
+void ozaki_free(Context* ctx, OzakiOperand& o) {
+    if (o.planes) cudaFreeAsync(o.planes, ctx->stream);
+    if (o.scale) dfree(ctx, o.scale);
+    o.planes = nullptr;
+    o.scale = nullptr;
+}
+
+// C(m x n, ldc) = A^T B from the digit planes of A^T (m rows) and B^T (n rows)
+void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, double* C,
+                    long long ldc) {
+    TNR_CHECK(A.K == B.K && A.slices == B.slices, "ozaki_multiply: operand mismatch");
+    CUtensorMap mapA, mapB;
+    TNR_CHECK(make_plane_map(&mapA, A.planes, A.rows, A.K, A.slices, OBM) &&
+                  make_plane_map(&mapB, B.planes, B.rows, B.K, B.slices, OBN),
+              "ozaki_multiply: tensor map encoding failed");
+    static bool configured = false;
+    if (!configured) {
+        TNR_CUDA(cudaFuncSetAttribute(ozaki_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)OSMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)((A.rows + OBM - 1) / OBM), (unsigned)((B.rows + OBN - 1) / OBN));
+    const int S = A.slices;
+    for (int t = S - 1; t >= 0; --t) {  // smallest weight first
+        OzakiParams p;
+        p.C = C; p.ldc = ldc;
+        p.scaleA = A.scale; p.scaleB = B.scale;
+        p.M = (int)A.rows; p.N = (int)B.rows; p.K = (int)A.K;
+        p.t = t;
+        p.weight = std::ldexp(1.0, -12 - 7 * t);
+        p.accumulate = (t != S - 1);
+        ozaki_group_kernel<<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
+        TNR_CUDA(cudaGetLastError());
+        ctx->ctr.launches++;
+        ctx->ctr.ozaki_launches++;
+    }
+    ctx->ctr.gemm_flops += 2.0 * A.rows * B.rows * (double)A.K;
+    ctx->ctr.ozaki_gemms++;
+}
+
+}  // namespace tnr

@@ -276,13 +276,19 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
     //  Qk_f[(z x1' x2), (a y1' y1)] = sum_x1  A1 * Ux[:, :, f]
     //  Pk_d[(z x1' x2), (y2 b y2')] = sum_x2' A2 * Ux[:, :, d]
     const long long kdim = Dz * Dx * Dx, mdim = Dz * Dy * Dy;
+    // opt-in: the chunk GEMM on the INT8 tensor cores (Ozaki scheme, gemm_ozaki.cu); operands
+    // are split into digit planes once per d / once per f and reused by all chunks
+    const bool oz = ozaki_applicable(ctx, mdim, mdim, kdim);
     DT A2p = permute(T, {3, 0, 1, 2, 4, 5});  // [X | z b Y y x]
     std::vector<DT> Pk;
+    std::vector<OzakiOperand> Pk8;
     Pk.reserve(nx);
     for (long long d = 0; d < nx; ++d) {
         DT Uxd = DT::view(ctx, Ux.p + d * Dx * Dx, {Dx, Dx});  // [x1' x2']
         DT Pn = contract(A2p, "XzbYyx", Uxd, "pX", "zbYyxp");
-        Pk.push_back(permute(Pn, {0, 5, 4, 3, 1, 2}));  // [z p x | y b Y]
+        DT Pd = permute(Pn, {0, 5, 4, 3, 1, 2});  // [z p x | y b Y]
+        if (oz) Pk8.push_back(ozaki_split(ctx, Pd.p, kdim, mdim, kdim));
+        else Pk.push_back(std::move(Pd));
     }
     A2p.release();
     const long long so[6] = {1, od[0], od[0] * od[1], od[0] * od[1] * od[2],
@@ -292,9 +298,28 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
         DT Qn = contract(T, "azYXyx", Uxf, "xq", "azYXyq");
         DT Qk = permute(Qn, {1, 3, 5, 0, 2, 4});  // [z X q | a Y y]
         Qn.release();
+        OzakiOperand Q8;
+        if (oz) {
+            Q8 = ozaki_split(ctx, Qk.p, kdim, mdim, kdim);
+            Qk.release();
+        }
         for (long long d = 0; d < nx; ++d) {
             // R[(a y1' y1), (y2 b y2')]
             DT R(ctx, {Dz * Dy, Dy * Dy, Dz * Dy});
+            if (oz) {
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (ctx->time_gemm) {
+                    TNR_CUDA(cudaEventCreate(&e0));
+                    TNR_CUDA(cudaEventCreate(&e1));
+                    TNR_CUDA(cudaEventRecord(e0, ctx->stream));
+                }
+                ozaki_multiply(ctx, Q8, Pk8[d], R.p, mdim);
+                if (ctx->time_gemm) {
+                    TNR_CUDA(cudaEventRecord(e1, ctx->stream));
+                    ctx->gemm_events.emplace_back(e0, e1);
+                    ctx->timed_flops += 2.0 * mdim * mdim * (double)kdim;
+                }
+            } else
             gemm(ctx, 'T', 'N', (int)mdim, (int)mdim, (int)kdim, 1.0, Qk.p, kdim, Pk[d].p, kdim,
                  0.0, R.p, mdim);
             // S[(a y1'), e, (b y2')] = sum_(y1 y2) R[(a y1'), (y1 y2), (b y2')] Uy[(y1 y2), e]
@@ -322,7 +347,9 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
                 strided_copy(ctx, W.p, Tout.p + off, 4, wd, ws, wdst);
             }
         }
+        if (oz) ozaki_free(ctx, Q8);
     }
+    for (auto& o : Pk8) ozaki_free(ctx, o);
 }
 
 // full step! (hotrg3d.jl:131-139) on one GPU
