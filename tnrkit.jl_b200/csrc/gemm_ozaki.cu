@@ -100,39 +100,45 @@ struct OzakiParams {
     const double* scaleA;  // 2^e per row of A^T
     const double* scaleB;  // 2^e per row of B^T
     int M, N, K;
-    int t;         // accumulation group: pairs (i, t - i), i = 0..t
-    double weight; // 2^(-12 - 7 t)
-    int accumulate;  // 0: C = value, 1: C += value
+    int S;         // digit planes; groups t = S-1 .. 0, group t = pairs (i, t - i), weight 2^(-12-7t)
 };
 
+// One CTA per 128 x 256 output tile.  All S accumulation groups of the tile run inside one
+// launch: the MMA thread alternates between two 256-column TMEM accumulators, the four epilogue
+// warps drain accumulator g (convert, scale, accumulate into FP64 C) while the MMAs of group
+// g + 1 are already running.
 __global__ void __launch_bounds__(OTHREADS, 1)
-ozaki_group_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const OzakiParams p) {
+ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const OzakiParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned long long* bars = (unsigned long long*)(smem + (size_t)OSTAGES * OSTAGE_BYTES);
     const unsigned full0 = o_smem_u32(bars), empty0 = o_smem_u32(bars + OSTAGES);
-    const unsigned tmem_full = o_smem_u32(bars + 2 * OSTAGES);
-    unsigned* tmem_ptr = (unsigned*)(bars + 2 * OSTAGES + 1);
+    const unsigned tfull0 = o_smem_u32(bars + 2 * OSTAGES);        // [2] accumulator ready
+    const unsigned tempty0 = o_smem_u32(bars + 2 * OSTAGES + 2);   // [2] accumulator drained
+    unsigned* tmem_ptr = (unsigned*)(bars + 2 * OSTAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * OBM, n0 = blockIdx.y * OBN;
     const int KB = (p.K + OBK - 1) / OBK;
-    const int total = KB * (p.t + 1);  // k-blocks over all plane pairs of this group
+    const int S = p.S;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OSTAGES; ++s) {
             o_mbar_init(full0 + 8 * s, 1);
             o_mbar_init(empty0 + 8 * s, 1);
         }
-        o_mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            o_mbar_init(tfull0 + 8 * b, 1);
+            o_mbar_init(tempty0 + 8 * b, 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                          o_smem_u32(tmem_ptr)),
-                     "n"(OTMEM_COLS)
+                     "n"(2 * OTMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -144,16 +150,19 @@ ozaki_group_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int i = 0; i <= p.t; ++i) {
-                const int j = p.t - i;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
-                    o_mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    unsigned full = full0 + 8 * s;
-                    o_mbar_expect_tx(full, OSTAGE_BYTES);
-                    unsigned dst = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
-                    o_tma_load_3d(dst, &mapA, kb * OBK, m0, i, full);
-                    o_tma_load_3d(dst + OA_BYTES, &mapB, kb * OBK, n0, j, full);
+            for (int g = 0; g < S; ++g) {
+                const int t = S - 1 - g;
+                for (int i = 0; i <= t; ++i) {
+                    const int j = t - i;
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
+                        o_mbar_wait(empty0 + 8 * s, ph ^ 1);
+                        unsigned full = full0 + 8 * s;
+                        o_mbar_expect_tx(full, OSTAGE_BYTES);
+                        unsigned dst = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
+                        o_tma_load_3d(dst, &mapA, kb * OBK, m0, i, full);
+                        o_tma_load_3d(dst + OA_BYTES, &mapB, kb * OBK, n0, j, full);
+                    }
                 }
             }
         }
@@ -162,55 +171,74 @@ ozaki_group_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             // D = S32, A = B = signed int8, both K-major, N = 256, M = 128
             const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) |
                                    ((unsigned)(OBN >> 3) << 17) | ((unsigned)(OBM >> 4) << 24);
-            for (int it = 0; it < total; ++it) {
-                int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
-                o_mbar_wait(full0 + 8 * s, ph);
+            int it = 0;
+            for (int g = 0; g < S; ++g) {
+                const int t = S - 1 - g, buf = g & 1;
+                o_mbar_wait(tempty0 + 8 * buf, ((g >> 1) & 1) ^ 1);  // accumulator drained
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                unsigned a_base = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
-                unsigned b_base = a_base + OA_BYTES;
+                const unsigned acc = tmem_base + (unsigned)(buf * OTMEM_COLS);
+                const int nblk = KB * (t + 1);
+                for (int b = 0; b < nblk; ++b, ++it) {
+                    int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
+                    o_mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    unsigned a_base = o_smem_u32(smem + (size_t)s * OSTAGE_BYTES);
+                    unsigned b_base = a_base + OA_BYTES;
 #pragma unroll
-                for (int k = 0; k < OBK / 32; ++k)
-                    o_umma_i8(tmem_base, o_make_desc(a_base + k * 32), o_make_desc(b_base + k * 32),
-                              idesc, (it > 0 || k > 0) ? 1u : 0u);
-                o_umma_commit(empty0 + 8 * s);
+                    for (int k = 0; k < OBK / 32; ++k)
+                        o_umma_i8(acc, o_make_desc(a_base + k * 32), o_make_desc(b_base + k * 32),
+                                  idesc, (b > 0 || k > 0) ? 1u : 0u);
+                    o_umma_commit(empty0 + 8 * s);
+                }
+                o_umma_commit(tfull0 + 8 * buf);
             }
-            o_umma_commit(tmem_full);
         }
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        o_mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const int row = m0 + q * 32 + lane;
-        const double sa = (row < p.M) ? p.scaleA[row] * p.weight : 0.0;
-        for (int c0 = 0; c0 < OBN; c0 += 16) {
-            unsigned v[16];
-            unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
-                  "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                  "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            if (row < p.M) {
+        const double sa = (row < p.M) ? p.scaleA[row] : 0.0;
+        for (int g = 0; g < S; ++g) {
+            const int t = S - 1 - g, buf = g & 1;
+            const double w = sa * exp2((double)(-12 - 7 * t));
+            o_mbar_wait(tfull0 + 8 * buf, (g >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int c0 = 0; c0 < OBN; c0 += 16) {
+                unsigned v[16];
+                unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) +
+                                 (unsigned)(buf * OTMEM_COLS + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                      "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                      "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (row < p.M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    int col = n0 + c0 + j;
-                    if (col < p.N) {
-                        double val = (double)(int)v[j] * (sa * p.scaleB[col]);
-                        double* cp = p.C + (long long)col * p.ldc + row;
-                        *cp = p.accumulate ? (*cp + val) : val;
+                    for (int j = 0; j < 16; ++j) {
+                        int col = n0 + c0 + j;
+                        if (col < p.N) {
+                            double val = (double)(int)v[j] * (w * p.scaleB[col]);
+                            double* cp = p.C + (long long)col * p.ldc + row;
+                            *cp = (g > 0) ? (*cp + val) : val;
+                        }
                     }
                 }
             }
+            // accumulator `buf` may be overwritten by group g + 2
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tempty0 + 8 * buf)
+                             : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
-                     "n"(OTMEM_COLS)
+                     "n"(2 * OTMEM_COLS)
                      : "memory");
     }
 }
@@ -324,25 +352,20 @@ void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, 
               "ozaki_multiply: tensor map encoding failed");
     static bool configured = false;
     if (!configured) {
-        TNR_CUDA(cudaFuncSetAttribute(ozaki_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TNR_CUDA(cudaFuncSetAttribute(ozaki_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)OSMEM));
         configured = true;
     }
     dim3 grid((unsigned)((A.rows + OBM - 1) / OBM), (unsigned)((B.rows + OBN - 1) / OBN));
-    const int S = A.slices;
-    for (int t = S - 1; t >= 0; --t) {  // smallest weight first
-        OzakiParams p;
-        p.C = C; p.ldc = ldc;
-        p.scaleA = A.scale; p.scaleB = B.scale;
-        p.M = (int)A.rows; p.N = (int)B.rows; p.K = (int)A.K;
-        p.t = t;
-        p.weight = std::ldexp(1.0, -12 - 7 * t);
-        p.accumulate = (t != S - 1);
-        ozaki_group_kernel<<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
-        TNR_CUDA(cudaGetLastError());
-        ctx->ctr.launches++;
-        ctx->ctr.ozaki_launches++;
-    }
+    OzakiParams p;
+    p.C = C; p.ldc = ldc;
+    p.scaleA = A.scale; p.scaleB = B.scale;
+    p.M = (int)A.rows; p.N = (int)B.rows; p.K = (int)A.K;
+    p.S = A.slices;
+    ozaki_tile_kernel<<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+    ctx->ctr.ozaki_launches++;
     ctx->ctr.gemm_flops += 2.0 * A.rows * B.rows * (double)A.K;
     ctx->ctr.ozaki_gemms++;
 }
