@@ -210,6 +210,8 @@ def run_gpu(args):
     import tnrkit.jl_b200 as tk
 
     ctx = tk.default_context()
+    if args.engine == "ozaki":
+        ctx.set_option("ozaki", args.ozaki_planes)
     chi = args.chi
     peak = measure_fp64_peak(torch, dev) if rank == 0 else None
 
@@ -290,8 +292,11 @@ def run_gpu(args):
             "metric": METRIC % chi, "value": sec, "unit": "s/RG-step", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if args.engine == "dmma" else
+            f"f64 emulated by {args.ozaki_planes} int8 digit planes (Ozaki scheme, tcgen05 kind::i8)",
+            "data": "synthetic",
             "config": {
+                "engine": args.engine,
                 "workload": f"HOTRG_3D on classical_ising_3D(Trivial, beta_c) truncrank({chi}); "
                             f"timed steps are RG iterations {args.warmup + 1}.."
                             f"{args.warmup + K} of run! (legs {scheme.T.dims})",
@@ -349,6 +354,10 @@ def main():
     ap.add_argument("--chi", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="dmma", choices=["dmma", "ozaki"],
+                    help="dmma: FP64 tensor cores (default, the measured configuration); ozaki: "
+                         "EXPERIMENTAL FP64 emulation of the chunk GEMM on the INT8 tensor cores")
+    ap.add_argument("--ozaki-planes", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

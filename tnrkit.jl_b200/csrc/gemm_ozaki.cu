@@ -119,7 +119,17 @@ ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     unsigned* tmem_ptr = (unsigned*)(bars + 2 * OSTAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * OBM, n0 = blockIdx.y * OBN;
+    // grouped tile order: the ~148 concurrently resident CTAs cover a near-square patch of
+    // output tiles, so every A / B plane tile is fetched from HBM once and reused from L2
+    const int tiles_m = (p.M + OBM - 1) / OBM, tiles_n = (p.N + OBN - 1) / OBN;
+    constexpr int GROUP = 12;
+    const int per_group = GROUP * tiles_n;
+    const int gid = blockIdx.x / per_group;
+    const int first_m = gid * GROUP;
+    const int gsz = min(tiles_m - first_m, GROUP);
+    const int tm = first_m + (blockIdx.x % per_group) % gsz;
+    const int tn = (blockIdx.x % per_group) / gsz;
+    const int m0 = tm * OBM, n0 = tn * OBN;
     const int KB = (p.K + OBK - 1) / OBK;
     const int S = p.S;
 
@@ -356,7 +366,7 @@ void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, 
                                       (int)OSMEM));
         configured = true;
     }
-    dim3 grid((unsigned)((A.rows + OBM - 1) / OBM), (unsigned)((B.rows + OBN - 1) / OBN));
+    dim3 grid((unsigned)(((A.rows + OBM - 1) / OBM) * ((B.rows + OBN - 1) / OBN)));
     OzakiParams p;
     p.C = C; p.ldc = ldc;
     p.scaleA = A.scale; p.scaleB = B.scale;
