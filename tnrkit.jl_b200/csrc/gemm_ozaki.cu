@@ -212,26 +212,38 @@ ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const double w = sa * exp2((double)(-12 - 7 * t));
             o_mbar_wait(tfull0 + 8 * buf, (g >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            for (int c0 = 0; c0 < OBN; c0 += 16) {
-                unsigned v[16];
+            for (int c0 = 0; c0 < OBN; c0 += 32) {
+                unsigned v[32];
                 unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) +
                                  (unsigned)(buf * OTMEM_COLS + c0);
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
                       "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                      "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                      "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+                      "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                 if (row < p.M) {
+                    // all loads of the old C values are issued before the first store, so the
+                    // 32 read-modify-writes overlap instead of paying 32 global latencies in turn
+                    double old[32];
+                    double* cp = p.C + (long long)(n0 + c0) * p.ldc + row;
+                    if (g > 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 32; ++j)
+                            old[j] = (n0 + c0 + j < p.N) ? __ldcg(cp + (long long)j * p.ldc) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
                         int col = n0 + c0 + j;
                         if (col < p.N) {
                             double val = (double)(int)v[j] * (w * p.scaleB[col]);
-                            double* cp = p.C + (long long)col * p.ldc + row;
-                            *cp = (g > 0) ? (*cp + val) : val;
+                            __stcg(cp + (long long)j * p.ldc, (g > 0) ? (old[j] + val) : val);
                         }
                     }
                 }
