@@ -289,16 +289,22 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
     if (amax > 0.0 && isfinite(amax)) e = ilogb(amax) + 1;  // amax * 2^-e in [0.5, 1)
     if (threadIdx.x == 0) scale[r] = ldexp(1.0, e);
     int8_t* out = planes + (long long)r * K;
-    for (int k = threadIdx.x; k < K; k += 256) {
-        double y = ldexp(x[k], 6 - e);  // |y| < 64
-        double q = rint(y);
-        out[k] = (int8_t)(int)q;
-        double rem = y - q;             // |rem| <= 0.5, exact
-        for (int i = 1; i < slices; ++i) {
-            rem *= 128.0;
-            q = rint(rem);
-            out[(long long)i * plane_stride + k] = (int8_t)(int)q;
-            rem -= q;
+    // 8 consecutive k per thread: one 64-byte read, one packed 8-byte store per digit plane
+    // (K is a multiple of 16, rows of the planes are 8-byte aligned)
+    for (int k8 = threadIdx.x * 8; k8 < K; k8 += 256 * 8) {
+        double rem[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rem[u] = ldexp(x[k8 + u], 6 - e) * (1.0 / 128.0);
+        for (int i = 0; i < slices; ++i) {
+            unsigned long long pack = 0ULL;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                double y = rem[u] * 128.0;     // exact
+                double q = rint(y);            // |q| <= 64
+                rem[u] = y - q;                // |rem| <= 0.5, exact
+                pack |= (unsigned long long)(unsigned char)(signed char)(int)q << (8 * u);
+            }
+            *reinterpret_cast<unsigned long long*>(out + (long long)i * plane_stride + k8) = pack;
         }
     }
 }
