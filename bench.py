@@ -325,10 +325,15 @@ def run_gpu(args):
                 # kernel (ncu --set full, gpurun_out/prof_gemm_tma_13824_r01.ncu-rep, summarised
                 # in profiles/r01_summary.md): 32.13 GB + 1.53 GB for 4.59 GB of operand+result
                 # bytes (operands re-read from L2, hit rate 81 %); 227 GB/s, 3 % of HBM
-                "traffic": 33.66e9 if chi == 24 else None, "traffic_unit": "bytes per launch",
-                "kernel": "gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
-                          "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
-                          "projector Gram GEMMs above 1e11 flop)", "launches_timed": gemm_n,
+                "traffic": 33.66e9 if (chi == 24 and args.engine == "dmma") else None,
+                "traffic_unit": "bytes per launch",
+                "kernel": ("gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
+                           "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
+                           "projector Gram GEMMs above 1e11 flop)") if args.engine == "dmma" else
+                          ("ozaki_tile_kernel (tcgen05.mma kind::i8, TMEM accumulators; achieved = "
+                           "FP64-EQUIVALENT flop rate of the emulated chunk contraction, so frac "
+                           "against the FP64 peak may exceed 1) + DMMA kernels for the Gram GEMMs"),
+                "launches_timed": gemm_n,
                 "tma_gemm_launches": ctr.get("tma_gemm_launches"),
                 "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (of measured; "
                                "MEASURED_PEAKS.json holds no FP64 figure); nominal FP64 tensor "
