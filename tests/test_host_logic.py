@@ -144,3 +144,12 @@ def test_charged_model_arrays(tk):
     assert p.N == 3 and p.charges[0] == (0, 1, 2)
     assert type(np.asarray(p)) is np.ndarray
     assert getattr(tk.classical_ising(tk.Trivial), "charges", None) is None
+
+
+def test_header_is_plain_c():
+    """include/tnrcuda.h must compile as C99 (it is what a Julia `ccall` / any FFI binds)."""
+    import subprocess
+
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "tnrcuda.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
