@@ -317,6 +317,11 @@ def run_gpu(args):
                 "free_energy": tk.free_energy(norms, tk.ising_βc_3D, scalefactor=8.0),
                 "free_energy_benchmark": -3.507,
                 "wall_s_timed_region": wall,
+                # not measured in this run: the opt-in INT8 emulation engine, for context
+                "experimental_ozaki_engine": None if args.engine == "ozaki" else {
+                    "s_per_rg_step_n1_chi24": 146.0,
+                    "how": "python bench.py --engine ozaki (separate run, same B200 pool)",
+                    "source": "profiles/r01_bench_n1_chi24_ozaki_experimental.json"},
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

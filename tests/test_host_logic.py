@@ -153,3 +153,24 @@ def test_header_is_plain_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
                         os.path.join(ROOT, "include", "tnrcuda.h")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("name,kind,dims,chi", [
+    ("TRG", 0, (2, 3, 3, 2), 4), ("TRG", 0, (4, 4, 4, 4), 5), ("BTRG", 1, (2, 3, 3, 2), 4),
+    ("BTRG", 1, (3, 3, 3, 3), 20), ("HOTRG", 2, (2, 3, 3, 2), 5), ("HOTRG", 2, (4, 4, 4, 4), 6),
+    ("ATRG", 3, (2, 3, 3, 2), 4), ("ATRG", 3, (3, 3, 3, 3), 5), ("ATRG", 3, (2, 2, 2, 2), 16),
+    ("HOTRG_3D", 4, (2, 2, 2, 2, 2, 2), 3), ("HOTRG_3D", 4, (2, 2, 3, 2, 3, 2), 5),
+    ("ATRG_3D", 5, (2, 2, 2, 2, 2, 2), 3), ("ATRG_3D", 5, (2, 2, 2, 2, 2, 2), 9),
+])
+def test_step_out_dims_matches_oracle_shapes(tk, name, kind, dims, chi):
+    """tnr_step_out_dims is pure host arithmetic: it must predict the leg dimensions the
+    reference algorithm produces (checked against the oracle on a random tensor)."""
+    from tnrkit.jl_b200 import _lib
+
+    lib = _lib.load()
+    out = (ctypes.c_int64 * len(dims))()
+    assert lib.tnr_step_out_dims(kind, _lib.i64(dims), chi, out) == 0
+    rng = np.random.default_rng(sum(dims) + chi)
+    s = getattr(o, name)(rng.random(dims) + 0.05)
+    s.step(chi)
+    assert tuple(out) == s.T.shape
