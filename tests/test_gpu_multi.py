@@ -45,6 +45,21 @@ def _worker(rank, world, port, chi, nsteps, q):
         v1 = C.c_double()
         ctx.call("tnr_get_counter", b"peer_scatter_launches", C.byref(v1))
         out[mode + "_peer_launches"] = v1.value - v0.value
+    # the opt-in INT8 engine inside the sharded step (chi = 8: 512^3 chunk contractions)
+    ref8 = tk.run(tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial)), tk.truncrank(8), tk.maxiter(2),
+                  verbosity=0)
+    ctx.set_option("ozaki", 8)
+    try:
+        g0 = C.c_double()
+        ctx.call("tnr_get_counter", b"ozaki_gemms", C.byref(g0))
+        oz8 = tk.run(tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial)), tk.truncrank(8),
+                     tk.maxiter(2), verbosity=0)
+        g1 = C.c_double()
+        ctx.call("tnr_get_counter", b"ozaki_gemms", C.byref(g1))
+    finally:
+        ctx.set_option("ozaki", 0)
+    out["ozaki_used"] = g1.value - g0.value
+    out["ozaki_maxrel"] = max(abs(a - b) / abs(b) for a, b in zip(oz8, ref8))
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -76,6 +91,7 @@ def test_hotrg3d_sharded_two_gpus():
             got = np.array(res[r][mode])
             assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-10, (r, mode)
         assert res[r]["nccl_peer_launches"] == 0
+        assert res[r]["ozaki_used"] > 0 and res[r]["ozaki_maxrel"] <= 1e-11
         # the two exchange mechanisms move the same numbers: bit-identical norm lists
         assert res[r]["peers"] == res[r]["nccl"]
     assert res[0]["nccl"] == res[1]["nccl"]  # replicas stay bit-identical
