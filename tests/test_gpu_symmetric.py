@@ -88,3 +88,41 @@ def test_block_sparse_schemes_match_oracle_and_dense(tk, name, chi, n, model):
     assert np.max(np.abs(got - dense) / np.abs(dense)) <= RTOL
     # the coarse-grained tensor stays block sparse: only symmetry-allowed blocks are stored
     assert s.T.nnz() < np.prod(s.T.dims)
+
+
+@pytest.mark.parametrize("model,N", [("ising_z2", 2), ("potts_z3", 3)])
+def test_retained_sector_spectra_match_sector_oracle(tk, model, N):
+    """The retained singular-value spectra, sector by sector, after several block-sparse TRG steps
+    against the sector-aware CPU oracle (TensorKit semantics: per-sector SVD, global truncrank)."""
+    import sym_oracle as so
+    from tnrkit.jl_b200 import symmetric
+
+    T = tk.classical_ising() if model == "ising_z2" else tk.classical_potts(3)
+    chi, n = 9, 5
+    s_gpu = tk.TRG(T)
+    got = tk.run(s_gpu, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
+    s_ref = so.TRG_sym(np.asarray(T), T.charges, T.signs, N)
+    ref = o.run(s_ref, chi, n)
+    assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= RTOL
+    for S_gpu, sp_ref in zip(symmetric.LAST_SPECTRA["trg"], s_ref.last_spectra):
+        assert sorted(S_gpu) == [c for c, _ in sp_ref]           # same sectors kept
+        for c, vals in sp_ref:
+            g = S_gpu[c].to_numpy()
+            assert g.shape == vals.shape                           # same multiplicity per sector
+            assert np.abs(g - vals).max() <= 1e-10 * vals.max()
+
+
+@pytest.mark.parametrize("name,chi,n,sf", [("TRG", 8, 5, 2.0), ("HOTRG", 6, 3, 4.0), ("ATRG", 7, 3, 4.0)])
+def test_coarse_grained_tensor_spectrum_matches_oracle(tk, name, chi, n, sf):
+    """Gauge-invariant content of the coarse-grained tensor itself: singular values of T viewed as
+    a (1 2 | 3 4) matrix after n steps, dense path vs oracle."""
+    T = tk.classical_ising(tk.Trivial, 0.41)
+    s = getattr(tk, name)(T)
+    tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
+    r = getattr(o, name)(T)
+    o.run(r, chi, n)
+    a = s.T.to_numpy()
+    sv_g = np.linalg.svd(a.reshape(a.shape[0] * a.shape[1], -1), compute_uv=False)
+    sv_r = np.linalg.svd(r.T.reshape(r.T.shape[0] * r.T.shape[1], -1), compute_uv=False)
+    k = min(chi, sv_r.size)
+    assert np.abs(sv_g[:k] - sv_r[:k]).max() <= 1e-9 * sv_r[0]

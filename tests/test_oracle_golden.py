@@ -63,3 +63,17 @@ def test_free_energy_and_driver_semantics():
     # free_energy: lnz = sum_i log(z_i) * sf^(x - i), x = 1 - log(initial)/log(sf)
     assert np.isclose(o.free_energy([np.e, np.e], 2.0), -(1.0 + 0.5) / 2.0)
     assert np.isclose(o.free_energy([np.e], 1.0, scalefactor=4.0, initial_size=4.0), -0.25)
+
+
+def test_sector_oracle_agrees_with_dense_oracle():
+    """Per-sector SVD + sector-global truncrank (TensorKit semantics, oracle/sym_oracle.py) gives
+    the same norm list as the dense SVD of the charge-basis tensor when no cut is degenerate."""
+    import sym_oracle as so
+
+    for T, N, q in ((o.classical_ising_z2basis(), 2, (0, 1)),):
+        s = so.TRG_sym(T, [q] * 4, (1, 1, -1, -1), N)
+        a = o.run(s, 8, 6)
+        b = o.run(o.TRG(T), 8, 6)
+        assert np.max(np.abs(np.array(a) - np.array(b)) / np.abs(b)) < 1e-11
+        sp1, sp2 = s.last_spectra
+        assert sum(len(v) for _, v in sp1) == 8 and sum(len(v) for _, v in sp2) == 8

@@ -351,13 +351,18 @@ def sym_trace_2d(T: SymTensor, w_leg0=None, w_leg1=None):
 # ------------------------------------------------------------------------------------
 # step! / finalize! bodies on block-sparse tensors (configs[2]: TRG / BTRG on Z2 / ZN)
 # ------------------------------------------------------------------------------------
+LAST_SPECTRA = {}  # scheme name -> list of {sector: DeviceTensor} kept by the latest step
+
+
 def trg_step_sym(T: SymTensor, chi: int) -> SymTensor:
     """step!(::TRG) on a Z_N tensor -- src/schemes/trg.jl:38-44 with per-sector SVD12."""
     U, S, V, _ = sym_svd_trunc(T, 2, chi)
+    LAST_SPECTRA["trg"] = [S]         # retained per-sector spectra of the step (for inspection)
     rs = vec_map(S, 1)
     A = U.scale_leg(2, rs)            # U * sqrt(s)      [a b k]
     B = V.scale_leg(0, rs)            # sqrt(s) * V      [k c d]
     U2, S2, V2, _ = sym_svd_trunc(T.permute((1, 3, 0, 2)), 2, chi)
+    LAST_SPECTRA["trg"].append(S2)
     rs2 = vec_map(S2, 1)
     Cc = U2.scale_leg(2, rs2)
     D = V2.scale_leg(0, rs2)
