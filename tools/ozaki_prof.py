@@ -1,0 +1,14 @@
+"""One emulated 13824^3 GEMM for ncu (ozaki_tile_kernel)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tnrkit.jl_b200 as tk
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 13824
+ctx = tk.default_context()
+ctx.set_option("ozaki", 8)
+A = torch.randn((n, n), dtype=torch.float64, device="cuda")
+B = torch.randn((n, n), dtype=torch.float64, device="cuda")
+C = torch.empty((n, n), dtype=torch.float64, device="cuda")
+for _ in range(2):
+    ctx.call("tnr_gemm_ozaki", n, n, n, A.data_ptr(), n, B.data_ptr(), n, C.data_ptr(), n)
+torch.cuda.synchronize()
