@@ -40,6 +40,30 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL prints "NCCL version ..." from
+# C code) also write to file descriptor 1, so the descriptor itself is pointed at stderr for the
+# duration of the run and the JSON line is written to the saved original descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def step_flops(chi: int) -> float:
     """Algorithmic FP64 flops of one steady-state RG step (all six legs = chi): per
     z-compression 2*chi^11 (the (f,d)-chunked A1*A2 contraction) + 2*2*chi^8 (Q and P)
@@ -168,7 +192,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "s/RG-step", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------
@@ -351,7 +375,7 @@ def run_gpu(args):
             "gpu_launches": ctr["launches"],
             "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -369,6 +393,7 @@ def main():
                          "EXPERIMENTAL FP64 emulation of the chunk GEMM on the INT8 tensor cores")
     ap.add_argument("--ozaki-planes", type=int, default=8)
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
