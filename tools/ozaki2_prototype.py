@@ -74,3 +74,50 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ----------------------------------------------------------------------------------------------
+# FP64-only CRT reconstruction (what the GPU epilogue / reconstruction kernel would execute):
+# no big integers, only exactly-representable double arithmetic on 32-bit limbs.
+# ----------------------------------------------------------------------------------------------
+def limbs32(x, n):
+    return [float((x >> (32 * j)) & 0xFFFFFFFF) for j in range(n)]
+
+
+def reconstruct_fp64(residues, ms):
+    """residues[i]: float64 array of c_i in [0, p_i).  Returns the symmetric lift of
+    sum_i c_i w_i mod P as float64 with absolute accuracy ~ P * 2^-60."""
+    P = math.prod(ms)
+    nl = (P.bit_length() + 31) // 32 + 1
+    W = [limbs32((P // p) * pow(P // p, -1, p), nl) for p in ms]
+    PL = limbs32(P, nl)
+    S = [sum(residues[i] * W[i][j] for i in range(len(ms))) for j in range(nl)]  # exact: < 2^44
+    # quotient q = round(x / P) from the two most significant non-zero limbs (|q| <= 256 N)
+    top = S[nl - 1] * 2.0 ** 32 + S[nl - 2] + S[nl - 3] * 2.0 ** -32
+    q = np.rint(top / (float(P) / 2.0 ** (32 * (nl - 2))))
+    R = [S[j] - q * PL[j] for j in range(nl)]                                    # exact: < 2^45
+    out = np.zeros_like(residues[0])
+    for j in reversed(range(nl)):
+        out = out * 2.0 ** 32 + R[j]       # Horner in FP64: error ~ 2^-53 of the partial sums
+    return out
+
+
+def check_reconstruction():
+    rng = np.random.default_rng(1)
+    ms = MODULI[:16]
+    P = math.prod(ms)
+    n = 4000
+    # random integers |x| < P/4 with a wide range of magnitudes
+    xs = [int(rng.integers(-2 ** 62, 2 ** 62)) * (1 << int(rng.integers(0, 60))) for _ in range(n)]
+    xs = [x % P if abs(x) < P // 4 else (x % (P // 4)) for x in xs]
+    xs = [x - P if x > P // 2 else x for x in xs]
+    res = [np.array([x % p for x in xs], dtype=np.float64) for p in ms]
+    got = reconstruct_fp64(res, ms)
+    err = max(abs(float(g) - float(x)) for g, x in zip(got, xs))
+    rel = max(abs(int(g) - x) / max(1, abs(x)) for g, x in zip(got, xs))
+    print(f"FP64 limb reconstruction: max abs error / P = {err / float(P):.2e}; max error relative "
+          f"to the value itself = {rel:.2e} (FP64 rounding of the exact integer is 1.1e-16)")
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "recon":
+    check_reconstruction()
