@@ -77,3 +77,26 @@ def test_sector_oracle_agrees_with_dense_oracle():
         assert np.max(np.abs(np.array(a) - np.array(b)) / np.abs(b)) < 1e-11
         sp1, sp2 = s.last_spectra
         assert sum(len(v) for _, v in sp1) == 8 and sum(len(v) for _, v in sp2) == 8
+
+
+def test_ozaki_model_digit_planes_are_error_free():
+    """CPU model of the opt-in INT8 engine: the digit expansion is exact (8 planes reproduce a
+    double to 2^-56 of the row maximum) and the emulated product is as accurate as DGEMM."""
+    import ozaki_model as om
+
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((7, 300)) * np.exp(rng.uniform(-8, 8, size=(7, 300)))
+    planes, scale = om.split(X, 8)
+    assert all(np.abs(p).max() <= 64 for p in planes)
+    rec = om.reconstruct(planes, scale)
+    # residual after 8 planes: |rem| <= 0.5 in units of 2^(-6-49) of the row scale 2^e
+    assert np.abs((rec - X) / scale[:, None]).max() <= 2.0 ** -56
+    assert np.all(scale >= np.abs(X).max(axis=1)) and np.all(scale <= 2 * np.abs(X).max(axis=1))
+    A = rng.standard_normal((40, 512)) * np.exp(rng.uniform(-9, 9, size=(40, 512)))
+    B = rng.standard_normal((30, 512)) * np.exp(rng.uniform(-9, 9, size=(30, 1)))
+    ref = A.astype(np.longdouble) @ B.T.astype(np.longdouble)
+    scale_ab = np.abs(A).astype(np.longdouble) @ np.abs(B.T).astype(np.longdouble)
+    e8 = float(np.max(np.abs(om.multiply(A, B, 8) - ref) / scale_ab))
+    e7 = float(np.max(np.abs(om.multiply(A, B, 7) - ref) / scale_ab))
+    ed = float(np.max(np.abs(A @ B.T - ref) / scale_ab))
+    assert e8 <= 2e-15 and ed <= 2e-15 and e7 <= 3e-13 and e8 < e7
