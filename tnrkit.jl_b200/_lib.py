@@ -137,6 +137,11 @@ class Context:
         self.h = h
         self.device = device
 
+    @property
+    def torch_device(self) -> str:
+        """Device string of the buffers this context's kernels may touch (always CUDA)."""
+        return f"cuda:{self.device}"
+
     def check(self, rc: int, what: str):
         if rc != 0:
             msg = self.lib.tnr_last_error(self.h)

@@ -311,7 +311,7 @@ class HOTRG_3D(TNRScheme):
         grp = self.group if self.group is not None else dist.group.WORLD
         bufs, hdls = [], []
         for _ in range(2):
-            t = symm_mem.empty(nelem, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+            t = symm_mem.empty(nelem, dtype=torch.float64, device=self.ctx.torch_device)
             hdls.append(symm_mem.rendezvous(t, group=grp))
             bufs.append(t)
         self._symm = (bufs, hdls)

@@ -156,7 +156,7 @@ class SymTensor:
                 continue
             nr = rt[c][-1][1] + rt[c][-1][2]
             nc = ct[c][-1][1] + ct[c][-1][2]
-            buf = torch.zeros(nr * nc, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+            buf = torch.zeros(nr * nc, dtype=torch.float64, device=self.ctx.torch_device)
             mats[c] = DeviceTensor(buf, (nr, nc), 1, self.ctx)
         rlook = {c: {k: (o, s) for k, o, s in v} for c, v in rt.items()}
         clook = {c: {k: (o, s) for k, o, s in v} for c, v in ct.items()}
@@ -235,7 +235,7 @@ def sym_contract(A: SymTensor, la: str, B: SymTensor, lb: str, lc: str) -> SymTe
         m, k = Am[c].dims
         k2, n = Bm[c].dims
         assert k == k2
-        buf = torch.empty(m * n, dtype=torch.float64, device=f"cuda:{ctx.device}")
+        buf = torch.empty(m * n, dtype=torch.float64, device=ctx.torch_device)
         Cm[c] = DeviceTensor(buf, (m, n), 1, ctx)
         probs.append(_lib.GemmProblem(m, n, k, Am[c].buf.data_ptr(), m, Bm[c].buf.data_ptr(), k,
                                       buf.data_ptr(), m))

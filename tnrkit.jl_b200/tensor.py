@@ -33,7 +33,7 @@ class DeviceTensor:
         torch = _torch()
         ctx = ctx or _lib.default_context()
         n = max(1, math.prod(int(d) for d in dims))
-        buf = torch.empty(n, dtype=torch.float64, device=f"cuda:{ctx.device}")
+        buf = torch.empty(n, dtype=torch.float64, device=ctx.torch_device)
         return cls(buf, dims, ncod, ctx)
 
     @classmethod
@@ -75,7 +75,7 @@ class DeviceTensor:
         return out
 
     def __repr__(self):
-        return f"DeviceTensor(dims={self.dims}, device=cuda:{self.ctx.device})"
+        return f"DeviceTensor(dims={self.dims}, device={self.ctx.torch_device})"
 
 
 def contract(A: DeviceTensor, la: str, B: DeviceTensor, lb: str, lc: str) -> DeviceTensor:
