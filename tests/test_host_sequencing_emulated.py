@@ -69,3 +69,63 @@ def test_emulated_2d_block_sparse_schemes_match_oracle(tk, emu, name, chi, n, mo
     ref = np.array(o.run(getattr(o, name)(np.asarray(T)), chi, n))
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
     assert s.T.nnz() < np.prod(s.T.dims)
+
+
+@pytest.mark.parametrize("name,chi,n", [("HOTRG_3D", 4, 3), ("HOTRG_3D", 6, 2), ("ATRG_3D", 4, 3),
+                                        ("ATRG_3D", 6, 2)])
+def test_emulated_3d_block_sparse_schemes_match_oracle(tk, emu, name, chi, n):
+    """HOTRG_3D / ATRG_3D on the Z2 tensor the reference's 3D testsets use (test/schemes.jl:8)."""
+    T = tk.classical_ising_3D()
+    s = getattr(tk, name)(T, symmetric=True)
+    assert s.sym and s.ctx is emu
+    got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+    ref = np.array(o.run(getattr(o, name)(np.asarray(T)), chi, n))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+    assert s.T.nnz() < np.prod(s.T.dims)
+    # arrows: HOTRG_3D reproduces the input spaces; ATRG_3D's new bonds are non-dual in the domain
+    # of H and in the codomain of Proj_2/4 (atrg3d.jl:68-82), which after its leg rotations gives
+    # S' (x) S <- S' (x) S' (x) S (x) S from the second step on
+    want = (1, -1, -1, -1, 1, 1) if name == "HOTRG_3D" else (-1, 1, 1, 1, -1, -1)
+    assert tuple(l.sign for l in s.T.legs) == want
+
+
+def test_emulated_hotrg3d_chunking_is_exact(tk, emu):
+    """Chunking the two open x-bonds (ragged chunks, cached and recomputed P_D) changes nothing."""
+    from tnrkit.jl_b200 import symmetric
+
+    T = tk.classical_ising_3D()
+    chi, n = 6, 3
+    base = np.array(tk.run(tk.HOTRG_3D(T, symmetric=True), tk.truncrank(chi), tk.maxiter(n),
+                           verbosity=0))
+    assert symmetric.LAST_PLAN["hotrg3d"]["chunks"] == 1
+    seen = set()
+    for budget in (10, 6 ** 6 * 2, 6 ** 6 * 3):
+        s = tk.HOTRG_3D(T, symmetric=True, max_chunk_elems=budget)
+        got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+        plan = symmetric.LAST_PLAN["hotrg3d"]
+        assert plan["chunks"] > 1
+        seen.add((plan["chunk_size"], plan["cached_P"]))
+        assert np.max(np.abs(got - base) / np.abs(base)) <= 1e-13
+    assert any(c for _, c in seen) and any(not c for _, c in seen), seen
+    assert any(sz == 2 for sz, _ in seen), seen     # 3-dimensional sectors in chunks of 2: ragged
+
+
+def test_sym_slice_and_scatter_roundtrip(tk, emu):
+    rng = np.random.default_rng(5)
+    legs = [tk.Leg({0: 3, 1: 2}, +1), tk.Leg({0: 2, 1: 3}, -1), tk.Leg({0: 5, 1: 4}, +1)]
+    a = _random_sym(rng, 2, legs)
+    A = tk.SymTensor.from_dense(a, 2, legs)
+    from tnrkit.jl_b200.symmetric import leg_chunks, sym_scatter, sym_slice, sym_zeros
+
+    out = sym_zeros(2, legs, emu)
+    chunks = leg_chunks(legs[2], 2)
+    assert chunks == [(0, 0, 2), (0, 2, 4), (0, 4, 5), (1, 0, 2), (1, 2, 4)]
+    for ch in chunks:
+        piece = sym_slice(A, 2, ch)
+        q, lo, hi = ch
+        off = legs[2].offsets[q]
+        dense = piece.to_dense()
+        assert dense.shape == (5, 5, hi - lo)
+        assert np.array_equal(dense, a[:, :, off + lo: off + hi])
+        sym_scatter(out, piece, {2: ch})
+    assert np.array_equal(out.to_dense(), a)

@@ -210,6 +210,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         if (m[i].s < m[js].s) js = i;
     CopyParams p{};
     if (js == 0) {
+        TNR_CHECK((int)m.size() - 1 <= MAXR, "strided_copy: too many index groups after merging");
         p.ni = m[0].n; p.si_s = m[0].s; p.si_d = m[0].d;
         p.rank = 0;
         for (size_t i = 1; i < m.size(); ++i) {
@@ -252,6 +253,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         long long outer = 1;
         for (size_t i = 1; i < m.size(); ++i) {
             if (i == js || i == i2 || i == j2) continue;
+            TNR_CHECK(p.rank < MAXR, "strided_copy: too many index groups after merging");
             p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
             p.rank++;
             outer *= m[i].n;

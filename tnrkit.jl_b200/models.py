@@ -15,8 +15,8 @@ import numpy as np
 
 class ChargedArray(np.ndarray):
     """Host tensor in the charge basis of a Z_N symmetry: `charges[leg][i]` is the irrep label
-    of index i of that leg, `signs[leg]` = +1 (codomain) / -1 (domain), and entries are nonzero
-    only where sum_leg sign*charge = 0 mod N -- the information a TensorKit
+    of index i of that leg, `signs[leg]` = +1 (codomain) / -1 (domain), negated for a dual space,
+    and entries are nonzero only where sum_leg sign*charge = 0 mod N -- the information a TensorKit
     `TensorMap{Float64, Vect[ZNIrrep{N}]}` carries in its spaces."""
 
     @classmethod
@@ -123,7 +123,9 @@ def classical_ising_3D(*args, J=1.0):
         W = np.array([[math.sqrt(x), math.sqrt(y)], [math.sqrt(x), -math.sqrt(y)]])
         t = np.einsum("ai,aj,ak,al,am,an->ijklmn", W, W, W, W, W, W)
         t = np.ascontiguousarray(np.transpose(t, (0, 3, 4, 5, 1, 2)))
-        return ChargedArray.wrap(t, 2, [(0, 1)] * 6, (1, 1, -1, -1, -1, -1))
+        # spaces after permute(t, ((1,4),(5,6,2,3))): S (x) S' <- S (x) S (x) S' (x) S'  (ising.jl:164);
+        # arrow of a leg = (+1 codomain / -1 domain) * (-1 if the space is dual)
+        return ChargedArray.wrap(t, 2, [(0, 1)] * 6, (1, -1, -1, -1, 1, 1))
     raise TypeError(f"classical_ising_3D: unsupported symmetry {sym}")
 
 

@@ -183,11 +183,51 @@ class ATRG(_Sym2D):
     _sym_step = "atrg_step_sym"
 
 
-class ATRG_3D(TNRScheme):
+class _Sym3D(_SymmetricMixin):
+    """3D schemes on block-sparse Z_N tensors.  Opt-in (`symmetric=True`, or a SymTensor) in this
+    round: without it a charged model tensor is stored densely in the charge basis, which gives
+    the same numbers unless the cut splits an exactly degenerate multiplet."""
+    _sym_step = None
+
+    def _init_sym3d(self, T, symmetric, ctx):
+        from .symmetric import SymTensor
+
+        if isinstance(T, SymTensor) or symmetric:
+            if not isinstance(T, SymTensor) and getattr(T, "charges", None) is None:
+                raise TypeError("symmetric=True needs a tensor in a charge basis "
+                                "(classical_ising_3D(Z2Irrep, ...))")
+            return self._init_sym(T, True, ctx)
+        self.sym = False
+        return False
+
+    def _sym_finalize(self):
+        from .symmetric import sym_trace_3d
+
+        n = abs(sym_trace_3d(self.T))
+        self.T.scale(1.0 / n)
+        return n
+
+
+class ATRG_3D(_Sym3D, TNRScheme):
     """3D Anisotropic TRG (atrg3d.jl)."""
     kind = _lib.TNR_ATRG_3D
     nlegs = 6
     _step_fn = "tnr_atrg3d_step"
+
+    def __init__(self, T, ctx=None, symmetric=None):
+        if not self._init_sym3d(T, symmetric, ctx):
+            TNRScheme.__init__(self, T, ctx)
+
+    def step(self, trunc):
+        if not self.sym:
+            return TNRScheme.step(self, trunc)
+        from .symmetric import atrg3d_step_sym
+
+        self.T = atrg3d_step_sym(self.T, _chi(trunc))
+        return self
+
+    def finalize(self):
+        return self._sym_finalize() if self.sym else TNRScheme.finalize(self)
 
 
 class BTRG(_SymmetricMixin, TNRScheme):
@@ -268,7 +308,7 @@ def allgather_last_leg(buf, dims, group=None):
     return buf
 
 
-class HOTRG_3D(TNRScheme):
+class HOTRG_3D(_Sym3D, TNRScheme):
     """3D Higher-Order TRG (hotrg3d.jl).
 
     With `torch.distributed` initialised (one process per GPU) and `shard=True`, every
@@ -280,9 +320,16 @@ class HOTRG_3D(TNRScheme):
     _step_fn = "tnr_hotrg3d_step"
     PERM = (5, 3, 1, 2, 0, 4)  # ((6,4),(2,3,1,5))
 
-    def __init__(self, T, ctx=None, shard=None, group=None, peer_scatter=None):
-        super().__init__(T, ctx)
+    def __init__(self, T, ctx=None, shard=None, group=None, peer_scatter=None, symmetric=None,
+                 max_chunk_elems=1 << 29):
         self.group = group
+        self.max_chunk_elems = int(max_chunk_elems)
+        if self._init_sym3d(T, symmetric, ctx):
+            if shard:
+                raise NotImplementedError("bond sharding of the block-sparse HOTRG_3D step")
+            self.shard = False
+            return
+        TNRScheme.__init__(self, T, ctx)
         if shard is None:
             try:
                 import torch.distributed as dist
@@ -361,9 +408,17 @@ class HOTRG_3D(TNRScheme):
 
     def step(self, trunc):
         chi = _chi(trunc)
+        if self.sym:
+            from .symmetric import hotrg3d_step_sym
+
+            self.T = hotrg3d_step_sym(self.T, chi, self.max_chunk_elems)
+            return self
         for _ in range(3):
             self._substep(chi)
         return self
+
+    def finalize(self):
+        return self._sym_finalize() if self.sym else TNRScheme.finalize(self)
 
 
 def finalize(scheme):

@@ -519,3 +519,210 @@ def atrg_step_sym(T: SymTensor, chi: int) -> SymTensor:
     """step!(::ATRG) on a Z_N tensor -- src/schemes/atrg.jl:37-45."""
     T = _atrg_half_sym(T, chi).permute((1, 3, 0, 2))
     return _atrg_half_sym(T, chi).permute((2, 0, 3, 1))
+
+
+# ------------------------------------------------------------------------------------
+# 3D schemes on block-sparse tensors (HOTRG_3D / ATRG_3D on `classical_ising_3D(Z2Irrep)`,
+# the tensor the reference's own 3D testsets run on: test/schemes.jl:8,365-383)
+# ------------------------------------------------------------------------------------
+NO_TRUNCATION = 10 ** 9   # truncrank large enough to keep every value (left_orth / right_orth)
+LAST_PLAN = {}            # how the latest chunked step was split (for inspection / tests)
+
+
+def sym_zeros(N, legs, ctx) -> SymTensor:
+    """All symmetry-allowed blocks, zero-initialised on the device."""
+    import torch
+
+    t = SymTensor(N, legs, {}, ctx)
+    for key in t.keys():
+        bd = t.block_dims(key)
+        buf = torch.zeros(max(1, math.prod(bd)), dtype=torch.float64, device=t.ctx.torch_device)
+        t.blocks[key] = DeviceTensor(buf, bd, None, t.ctx)
+    return t
+
+
+def leg_chunks(leg: Leg, size: int):
+    """[(charge, lo, hi)] tiling every sector of `leg` into index ranges of at most `size`."""
+    out = []
+    for q in leg.charges:
+        d = leg.dims[q]
+        for lo in range(0, d, size):
+            out.append((q, lo, min(d, lo + size)))
+    return out
+
+
+def sym_slice(T: SymTensor, axis: int, chunk) -> SymTensor:
+    """T restricted to indices [lo, hi) of sector q of leg `axis` (compact copies of the blocks)."""
+    q, lo, hi = chunk
+    legs = list(T.legs)
+    legs[axis] = Leg({q: hi - lo}, T.legs[axis].sign)
+    out = SymTensor(T.N, legs, {}, T._ctx)
+    for key, blk in T.blocks.items():
+        if key[axis] != q:
+            continue
+        bd = list(T.block_dims(key))
+        st = _colmajor_strides(bd)
+        src = C.c_void_p(blk.buf.data_ptr() + 8 * lo * st[axis])
+        bd[axis] = hi - lo
+        piece = DeviceTensor.empty(bd, None, T.ctx)
+        T.ctx.call("tnr_strided_copy", src, piece.ptr, len(bd), _lib.i64(bd), _lib.i64(st),
+                   _lib.i64(_colmajor_strides(bd)))
+        out.blocks[key] = piece
+    return out
+
+
+def sym_scatter(out: SymTensor, piece: SymTensor, where):
+    """Writes `piece` (whose legs `axis` in `where` = {axis: (q, lo, hi)} are chunks) into the
+    matching index ranges of the blocks of `out`."""
+    for key, blk in piece.blocks.items():
+        dst_blk = out.blocks[key]
+        bd = piece.block_dims(key)
+        dst_st = _colmajor_strides(out.block_dims(key))
+        off = sum(lo * dst_st[ax] for ax, (_, lo, _) in where.items())
+        dst = C.c_void_p(dst_blk.buf.data_ptr() + 8 * off)
+        out.ctx.call("tnr_strided_copy", blk.ptr, dst, len(bd), _lib.i64(bd),
+                     _lib.i64(_colmajor_strides(bd)), _lib.i64(dst_st))
+
+
+def sym_trace_3d(T: SymTensor) -> float:
+    """sum T[1 1; 2 3 2 3]  (finalize!(::HOTRG_3D / ::ATRG_3D), src/utility/finalize.jl:56-66)."""
+    total = 0.0
+    for key, blk in T.blocks.items():
+        if key[0] != key[1] or key[2] != key[4] or key[3] != key[5]:
+            continue
+        d = T.block_dims(key)
+        assert d[0] == d[1] and d[2] == d[4] and d[3] == d[5]
+        st = _colmajor_strides(d)
+        s = C.c_double()
+        T.ctx.call("tnr_strided_sum", blk.ptr, 3, _lib.i64((d[0], d[2], d[3])),
+                   _lib.i64((st[0] + st[1], st[2] + st[4], st[3] + st[5])), None, C.byref(s))
+        total += s.value
+    return total
+
+
+def _hotrg3d_xproj_sym(A1: SymTensor, A2: SymTensor, chi: int) -> SymTensor:
+    """_get_hotrg3d_xproj (hotrg3d.jl:87-100): eigh_trunc! of MMdag (open leg 6) and of MdagM
+    (open leg 4), keep the one with the smaller truncation error.  Bosonic sectors: the twists
+    of hotrg3d.jl:55-56,76-77 are identities."""
+    A1c, A2c = sym_conj(A1), sym_conj(A2)
+    # MM[x2 z z' x2'] := A2[z z2; Y2 X2 y2 x2] conj(A2'[z' z2; Y2 X2 y2 x2'])   (hotrg3d.jl:57-58)
+    m2 = sym_contract(A2, "zabcdx", A2c, "wabcdy", "zxwy")
+    m1 = sym_contract(A1, "azbcdx", A1c, "awbcdy", "zxwy")
+    U, _, e = sym_eigh_trunc(sym_contract(m1, "zawc", m2, "zbwd", "abcd"), 2, chi)
+    # MM[x2 z z' x2'] := conj(A2[z z2; Y2 x2 y2 X2]) A2'[z' z2; Y2 x2' y2 X2]   (hotrg3d.jl:78-79)
+    m2 = sym_contract(A2c, "zabxcd", A2, "wabycd", "zxwy")
+    m1 = sym_contract(A1c, "azbxcd", A1, "awbycd", "zxwy")
+    U2, _, e2 = sym_eigh_trunc(sym_contract(m1, "zawc", m2, "zbwd", "abcd"), 2, chi)
+    return U2 if e > e2 else U
+
+
+def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> SymTensor:
+    """_step!(::HOTRG_3D) on a Z_N tensor -- src/schemes/hotrg3d.jl:102-129.
+
+    The chi^8 intermediate of the pairwise contraction order is never formed beyond `max_elems`
+    doubles: the two new open x-bonds (-4 and -6) are chunked, every (F, D) pair of chunks is
+    contracted on its own and scattered into the index ranges [.., D, .., F] of the output
+    blocks (same chunking as the dense engine, csrc/schemes.cu: hotrg3d_substep)."""
+    Ux = _hotrg3d_xproj_sym(T, T, chi)
+    yperm = (0, 1, 3, 2, 5, 4)   # ((1,2),(4,3,6,5)), hotrg3d.jl:109
+    Ty = T.permute(yperm)
+    Uy = _hotrg3d_xproj_sym(Ty, Ty, chi)
+    del Ty
+    Uxc, Uyc = sym_conj(Ux), sym_conj(Uy)
+    # T[-1 -2;-3 -4 -5 -6] := conj(Ux[x1 x2;-6]) Ux[x1' x2';-4] conj(Uy[y1 y2;-5]) Uy[y1' y2';-3]
+    #                          A1[-1 z; y1' x1' y1 x1] A2[z -2; y2' x2' y2 x2]      (hotrg3d.jl:116-120)
+    d = T.dims
+    bx, by = Ux.legs[2], Uy.legs[2]
+    out_legs = [T.legs[0], T.legs[1], by, bx, by.flipped(), bx.flipped()]
+    base = d[0] * d[2] * d[4] * d[1] * d[2] * d[4] / max(1, T.N)   # R per unit |F||D|
+    c = int(math.sqrt(max(1.0, max_elems / max(1.0, base))))
+    if c >= max(bx.dims.values()):
+        chunks = [None]
+    else:
+        chunks = leg_chunks(bx, max(1, c))
+
+    def Pd(D):
+        u = Ux if D is None else sym_slice(Ux, 2, D)
+        return sym_contract(T, "zbstuw", u, "qtd", "zbsuwqd")      # [z b y2' y2 x2 x1' d]
+
+    cache = T.nnz() * bx.total <= 4 * max_elems     # all P_D together: nnz(T) * |x-bond| doubles
+    LAST_PLAN["hotrg3d"] = {"chunks": len(chunks), "chunk_size": c, "cached_P": bool(cache)}
+    P = [Pd(D) for D in chunks] if cache else None
+    out = None if chunks == [None] else sym_zeros(T.N, out_legs, T.ctx)
+    for F in chunks:
+        u = Uxc if F is None else sym_slice(Uxc, 2, F)
+        Q = sym_contract(T, "azpqrx", u, "xwf", "azpqrwf")         # [a z y1' x1' y1 x2 f]
+        for j, D in enumerate(chunks):
+            R = sym_contract(Q, "azpqrwf", P[j] if cache else Pd(D), "zbsuwqd", "aprfbsud")
+            R = sym_contract(R, "aprfbsud", Uyc, "rue", "apfbsde")
+            R = sym_contract(R, "apfbsde", Uy, "psc", "abcdef")
+            if out is None:
+                return R
+            sym_scatter(out, R, {3: D, 5: F})
+    return out
+
+
+def hotrg3d_step_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> SymTensor:
+    """step!(::HOTRG_3D) on a Z_N tensor -- src/schemes/hotrg3d.jl:131-139."""
+    for _ in range(3):
+        T = hotrg3d_substep_sym(T, chi, max_elems).permute((5, 3, 1, 2, 0, 4))  # ((6,4),(2,3,1,5))
+    return T
+
+
+def _orth_r(Z: SymTensor, ncod: int) -> SymTensor:
+    """The factor `R` of `left_orth(Z)` up to the orthogonal gauge on its bond (which cancels
+    in atrg3d.jl:58-66): Sigma V^T of the untruncated per-sector SVD.  Legs [r(+), dom...]."""
+    _, S, Vt, _ = sym_svd_trunc(Z, ncod, NO_TRUNCATION)
+    return Vt.scale_leg(0, S)
+
+
+def _atrg3d_projectors_sym(Rl: SymTensor, Rr: SymTensor, chi: int):
+    """atrg3d.jl:58-66: temp = Rl Rr; U S V = svd_trunc(temp);
+    Pa[p q; k] = Rr V' S^-1/2,  Pb[k; p q] = S^-1/2 U' Rl."""
+    t = sym_contract(Rl, "ipq", Rr, "pqj", "ij")
+    U, S, V, _ = sym_svd_trunc(t, 1, chi)
+    inv = vec_map(S, 2, -0.5)
+    Pa = sym_contract(Rr, "pqj", sym_conj(V), "kj", "pqk").scale_leg(2, inv)
+    Pb = sym_contract(sym_conj(U), "ik", Rl, "ipq", "kpq").scale_leg(0, inv)
+    return Pa, Pb
+
+
+def atrg3d_substep_sym(T: SymTensor, chi: int) -> SymTensor:
+    """_step!(::ATRG_3D) on a Z_N tensor -- src/schemes/atrg3d.jl:34-83.  `permute(X, ((4,1),(2,3)))`
+    of the reference is expressed through leg labels instead of data movement, as in the dense
+    engine (csrc/schemes.cu: atrg3d_substep)."""
+    perm = (1, 4, 5, 2, 3, 0)   # ((2,5,6),(3,4,1))
+    fU, fS, fV, _ = sym_svd_trunc(T.permute(perm), 3, chi)     # U [i2 i5 i6 k], V [k i3 i4 i1]
+    US = sym_clone(fU).scale_leg(3, fS)
+    SV = sym_clone(fV).scale_leg(0, fS)
+    # M[-1 -2;-3 -4 -5 -6] := B[1 -2;-3 -4] C[-1 1;-5 -6], produced directly as permute(M, perm)
+    Mp = sym_contract(US, "iefa", SV, "bcdi", "befcda")
+    del US, SV
+    gU, gS, gV, _ = sym_svd_trunc(Mp, 3, chi)                   # U [m2 m5 m6 k], V [k m3 m4 m1]
+    del Mp
+    rs = vec_map(gS, 1)
+    gU.scale_leg(3, rs)    # X
+    gV.scale_leg(0, rs)    # Y
+    # AX[-1 -2;-3 -4 -5 -6] := A[1 -2;-3 -5] X[-1 1;-4 -6];  YD := Y[1 -2;-3 -5] D[-1 1;-4 -6]
+    AX = sym_contract(gU, "idfa", fU, "bcei", "abcdef")
+    YD = sym_contract(fV, "idfa", gV, "bcei", "abcdef")
+    q = (0, 1, 4, 5, 2, 3)
+    R1 = _orth_r(YD, 4)                                  # [r; 5 6]
+    R2 = _orth_r(AX, 4).permute((1, 2, 0))               # [5 6; r]
+    R3 = _orth_r(YD.permute(q), 4)                       # [r; 3 4]
+    R4 = _orth_r(AX.permute(q), 4).permute((1, 2, 0))    # [3 4; r]
+    P1, P2 = _atrg3d_projectors_sym(R1, R2, chi)
+    P3, P4 = _atrg3d_projectors_sym(R3, R4, chi)
+    # H[-1 -2;-3 -4] := YD[-1 -2;1 2 3 4] Proj_3[1 2;-3] Proj_1[3 4;-4]
+    H = sym_contract(sym_contract(YD, "abijkl", P3, "ijc", "abklc"), "abklc", P1, "kld", "abcd")
+    # G[-1 -2;-3 -4] := AX[-1 -2;1 2 3 4] Proj_4[-3;1 2] Proj_2[-4;3 4]
+    G = sym_contract(sym_contract(AX, "abijkl", P4, "cij", "abklc"), "abklc", P2, "dkl", "abcd")
+    # T[-1 -2;-3 -4 -5 -6] := G[1 -2;-5 -6] H[-1 1;-3 -4]
+    return sym_contract(H, "aicd", G, "ibef", "abcdef")
+
+
+def atrg3d_step_sym(T: SymTensor, chi: int) -> SymTensor:
+    """step!(::ATRG_3D) on a Z_N tensor -- src/schemes/atrg3d.jl:85-97."""
+    for _ in range(3):
+        T = atrg3d_substep_sym(T, chi).permute((3, 5, 1, 4, 0, 2))   # ((4,6),(2,5,1,3))
+    return T
