@@ -50,3 +50,13 @@ def test_block_sparse_hotrg3d_chunking_is_exact(tk):
 def test_symmetric_flag_requires_charges(tk):
     with pytest.raises(TypeError):
         tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), symmetric=True)
+
+
+@pytest.mark.parametrize("name,chi,rtol", [("HOTRG_3D", 8, 1.0e-3), ("ATRG_3D", 12, 5.0e-3)])
+def test_reference_3d_testsets_block_sparse(tk, name, chi, rtol):
+    """test/schemes.jl:365-383 as the reference runs them: `T_3D = classical_ising_3D()` is the
+    Z2Irrep tensor, so TensorKit works block by block -- here through the block-sparse path."""
+    s = getattr(tk, name)(tk.classical_ising_3D(), symmetric=True)
+    data = tk.run(s, tk.truncrank(chi), tk.maxiter(25), verbosity=0)
+    fs = tk.free_energy(data, tk.ising_βc_3D, scalefactor=8.0)
+    assert abs(fs - o.f_benchmark3D) <= rtol * abs(o.f_benchmark3D)
