@@ -142,6 +142,12 @@ int tnr_contract(tnr_context* ctx, const double* A, int rankA, const int64_t* di
  * k = min(chi, min(rows, cols)).  U: rows x k, S: k, Vt: k x cols, eps: 2-norm of discarded. */
 int tnr_svd_trunc(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
                   int chi, double* U, double* S, double* Vt, int64_t* k_out, double* eps_out);
+/* The factor R of `_, R = left_orth(T)` (src/schemes/atrg3d.jl:53-56) for a tall matricization
+ * (rows = first `ncod` legs >= cols), up to the orthogonal gauge on its new bond, which cancels
+ * in the projectors built from it (atrg3d.jl:58-66): R = Sigma V^T, cols x cols, R^T R = T^T T.
+ * The isometry Q is never formed.  Used chunk by chunk (TSQR) by the factored ATRG_3D step. */
+int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
+               double* R);
 /* eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) (src/schemes/hotrg.jl:106,114,
  * hotrg3d.jl:94-98).  Keeps the chi eigenvalues of largest magnitude.  MM is n x n and is
  * not modified.  W: k signed eigenvalues, V: n x k. */

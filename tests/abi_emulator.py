@@ -185,6 +185,12 @@ class EmulatedContext:
         C.cast(k_out, C.POINTER(C.c_int64))[0] = k
         C.cast(eps_out, C.POINTER(C.c_double))[0] = float(np.linalg.norm(s[k:]))
 
+    def _tnr_orth_r(self, T, rank, dims, ncod, R):
+        d = [dims[i] for i in range(rank)]
+        m, n = int(np.prod(d[:ncod])), int(np.prod(d[ncod:]))
+        assert m >= n, "orth_r: expects a tall matrix"
+        _f(R, (n, n))[...] = np.linalg.qr(_f(T, (m, n)), mode="r")
+
     def _tnr_eigh_trunc(self, MM, n, chi, W, V, k_out, eps_out):
         M = _f(MM, (n, n))
         w, v = np.linalg.eigh(0.5 * (M + M.T))

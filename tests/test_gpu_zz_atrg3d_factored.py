@@ -1,0 +1,116 @@
+"""Device twin of tests/test_atrg3d_factored_emulated.py: the factored ATRG_3D step
+(tnrkit.jl_b200/atrg3d_factored.py) through the real C ABI -- `tnr_orth_r`, the implicit products,
+the subspace-iteration SVD, chunked TSQR -- against the oracle, against the dense device step
+(`tnr_atrg3d_step`) and, on a box with 2 GPUs, sharded over NCCL.
+
+(File name: sorted after the other `-m gpu` files so that they run first under `-x`.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import tnr_oracle as o
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_orth_r_gram_identity(tk, ctx):
+    """tnr_orth_r: R^T R = T^T T (R is defined up to an orthogonal factor on the left)."""
+    from tnrkit.jl_b200 import _lib
+
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((6, 5, 4, 3, 2)) * np.logspace(0, -5, 6).reshape(3, 2)
+    T = tk.DeviceTensor.from_numpy(a)
+    R = tk.DeviceTensor.empty((6, 6), 1, ctx)
+    ctx.call("tnr_orth_r", T.ptr, 5, _lib.i64(a.shape), 3, R.ptr)
+    A = a.reshape((120, 6), order="F")
+    r = R.to_numpy()
+    assert np.abs(r.T @ r - A.T @ A).max() <= 1e-13 * np.abs(A.T @ A).max()
+    with pytest.raises(tk.TNRCudaError):
+        ctx.call("tnr_orth_r", T.ptr, 5, _lib.i64(a.shape), 1, R.ptr)   # 6 x 120: not tall
+
+
+@pytest.mark.parametrize("chi,n,block", [(4, 3, None), (6, 3, None), (6, 3, 14), (10, 2, 24)])
+def test_factored_atrg3d_matches_oracle_on_device(tk, ctx, chi, n, block):
+    from tnrkit.jl_b200 import atrg3d_factored as af
+
+    T = tk.classical_ising_3D(tk.Trivial)
+    s = tk.ATRG_3D(T, factored=True, block=block)
+    got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+    ref = np.array(o.run(o.ATRG_3D(T), chi, n))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+    if block is not None:
+        assert all(not st["dense"] for st in af.LAST_STATS["svd"])
+    assert s.T.dims == (chi,) * 6
+
+
+def test_factored_equals_dense_device_step(tk, ctx):
+    """chi = 12 (the reference's ATRG_3D testset size, test/schemes.jl): the factored step with
+    chunked TSQR against `tnr_atrg3d_step` on the same device, both at FP64."""
+    from tnrkit.jl_b200 import atrg3d_factored as af
+
+    T = tk.classical_ising_3D(tk.Trivial)
+    chi, n = 12, 3
+    dense = np.array(tk.run(tk.ATRG_3D(T, factored=False), tk.truncrank(chi), tk.maxiter(n),
+                            verbosity=0))
+    s = tk.ATRG_3D(T, factored=True, max_chunk_elems=12 ** 5 * 5)     # chunks of 5, 5, 2
+    got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+    assert af.LAST_STATS["chunks"]["AX"] == [3]
+    assert np.max(np.abs(got - dense) / np.abs(dense)) <= RTOL
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, chi, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    import tnrkit.jl_b200 as tk
+
+    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=True, max_chunk_elems=chi ** 5)
+    got = tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
+    q.put((rank, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_factored_atrg3d_sharded_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import tnrkit.jl_b200 as tk
+
+    chi, n = 5, 2      # ragged ownership of the open bond: 3 + 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, chi, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = np.array(o.run(o.ATRG_3D(tk.classical_ising_3D(tk.Trivial)), chi, n))
+    for r in range(2):
+        got = np.array(res[r])
+        assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL, r
+    assert np.max(np.abs(np.array(res[0]) - np.array(res[1]))) <= 1e-12 * np.max(np.abs(ref))

@@ -305,6 +305,17 @@ int tnr_svd_trunc(tnr_context* ctx, const double* T, int rank, const int64_t* di
     });
 }
 
+int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
+               double* R) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(ncod >= 1 && ncod < rank, "orth_r: bad arguments");
+        DT t = in_view(&ctx->c, T, to_dims(dims, rank));
+        DT r = orth_r(t, ncod);
+        copy_out(&ctx->c, r, R, nullptr);
+    });
+}
+
 int tnr_eigh_trunc(tnr_context* ctx, const double* MM, int64_t n, int chi, double* W, double* V,
                    int64_t* k_out, double* eps_out) {
     if (!ctx) return 1;

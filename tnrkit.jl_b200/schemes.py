@@ -209,25 +209,105 @@ class _Sym3D(_SymmetricMixin):
 
 
 class ATRG_3D(_Sym3D, TNRScheme):
-    """3D Anisotropic TRG (atrg3d.jl)."""
+    """3D Anisotropic TRG (atrg3d.jl).
+
+    `factored=True` keeps the tensor in the two-factor form `G * H` in which `_step!` produces it
+    and never builds a chi^6 object (tnrkit.jl_b200/atrg3d_factored.py): truncated SVDs by
+    subspace iteration on the implicit operator, R factors by TSQR over chunks of an open bond.
+    `factored=None` switches to it by itself when the dense step's chi^6 tensors would not fit in
+    HBM (chi >= 40).  With `shard=True` under torch.distributed (one process per GPU) the chunks
+    of the open bond are divided between the ranks (all-gather of the chunk R factors and of
+    H / G; nothing else is exchanged)."""
     kind = _lib.TNR_ATRG_3D
     nlegs = 6
     _step_fn = "tnr_atrg3d_step"
+    DENSE_BYTES_LIMIT = 150e9
 
-    def __init__(self, T, ctx=None, symmetric=None):
-        if not self._init_sym3d(T, symmetric, ctx):
-            TNRScheme.__init__(self, T, ctx)
+    def __init__(self, T, ctx=None, symmetric=None, factored=None, shard=None, group=None,
+                 max_chunk_elems=1 << 28, tol=1e-13, block=None):
+        self._F = None
+        self.block = block
+        self.factored = factored
+        self.group = group
+        self.max_chunk_elems = int(max_chunk_elems)
+        self.tol = float(tol)
+        if self._init_sym3d(T, symmetric, ctx):
+            if factored or shard:
+                raise NotImplementedError("factored / sharded ATRG_3D on block-sparse tensors")
+            self.factored = self.shard = False
+            return
+        TNRScheme.__init__(self, T, ctx)
+        if shard and factored is False:
+            raise ValueError("ATRG_3D: shard=True needs the factored step")
+        if shard:
+            self.factored = True
+        self.shard = bool(shard)
+        if self.factored:
+            self._to_factored()
+
+    @classmethod
+    def wants_factored(cls, chi: int) -> bool:
+        """The dense step holds up to 6 tensors of chi^6 doubles at once (T, AX, YD, a permuted
+        copy, the work copy of the R factorization, the result); beyond DENSE_BYTES_LIMIT (of
+        the 180 GB of HBM) the factored step takes over: chi >= 40."""
+        return 6 * 8.0 * float(chi) ** 6 > cls.DENSE_BYTES_LIMIT
+
+    # `T` stays the reference's field: with the factored state it is materialised on request
+    @property
+    def T(self):
+        if self._F is not None:
+            return self._F.to_dense()
+        return self._T
+
+    @T.setter
+    def T(self, value):
+        self._T = value
+        self._F = None
+
+    @property
+    def factors(self):
+        """The TwoFactor state of the factored step (None on the dense path)."""
+        return self._F
+
+    def _to_factored(self):
+        if self._F is None:
+            from .atrg3d_factored import TwoFactor
+
+            self._F = TwoFactor.from_dense(self._T)
+            self._T = None
 
     def step(self, trunc):
-        if not self.sym:
-            return TNRScheme.step(self, trunc)
-        from .symmetric import atrg3d_step_sym
+        chi = _chi(trunc)
+        if self.sym:
+            from .symmetric import atrg3d_step_sym
 
-        self.T = atrg3d_step_sym(self.T, _chi(trunc))
+            self.T = atrg3d_step_sym(self.T, chi)
+            return self
+        if self.factored is None:
+            self.factored = self.wants_factored(chi)
+        if not self.factored:
+            return TNRScheme.step(self, trunc)
+        from .atrg3d_factored import atrg3d_step_factored
+
+        self._to_factored()
+        self._F = atrg3d_step_factored(self._F, chi, max_chunk_elems=self.max_chunk_elems,
+                                       shard=self.shard, group=self.group, tol=self.tol,
+                                       block=self.block)
         return self
 
     def finalize(self):
-        return self._sym_finalize() if self.sym else TNRScheme.finalize(self)
+        if self.sym:
+            return self._sym_finalize()
+        if self._F is not None:
+            n = abs(self._F.trace_3d())
+            self._F.scale(1.0 / n)
+            return n
+        return TNRScheme.finalize(self)
+
+    def __repr__(self):
+        if self._F is not None:
+            return f"ATRG_3D(T: {self._F.dims}, factored, bond {self._F.bond_dim})"
+        return TNRScheme.__repr__(self)
 
 
 class BTRG(_SymmetricMixin, TNRScheme):
@@ -475,7 +555,7 @@ def beta_sweep(scheme_cls, model, betas, trscheme, criterion, **scheme_kwargs):
     mine = {}
     for i in range(rank, len(betas), world):
         kw = dict(scheme_kwargs)
-        if scheme_cls is HOTRG_3D:
+        if scheme_cls in (HOTRG_3D, ATRG_3D):
             kw["shard"] = False
         scheme = scheme_cls(model(betas[i]), **kw)
         mine[i] = run(scheme, trscheme, criterion, verbosity=0)

@@ -78,11 +78,17 @@ class DeviceTensor:
         return f"DeviceTensor(dims={self.dims}, device={self.ctx.torch_device})"
 
 
-def contract(A: DeviceTensor, la: str, B: DeviceTensor, lb: str, lc: str) -> DeviceTensor:
-    """One binary `@tensor` contraction by leg labels on the device (tnr_contract)."""
+def contract(A: DeviceTensor, la: str, B: DeviceTensor, lb: str, lc: str,
+             out: DeviceTensor | None = None) -> DeviceTensor:
+    """One binary `@tensor` contraction by leg labels on the device (tnr_contract).
+    `out`: write into this tensor (e.g. a slab view of a larger buffer) instead of a new one."""
     da = dict(zip(la, A.dims))
     da.update(zip(lb, B.dims))
-    out = DeviceTensor.empty([da[c] for c in lc], None, A.ctx)
+    od = tuple(da[c] for c in lc)
+    if out is None:
+        out = DeviceTensor.empty(od, None, A.ctx)
+    elif tuple(out.dims) != od:
+        raise ValueError(f"contract: out has dims {out.dims}, expected {od}")
     A.ctx.call("tnr_contract", A.ptr, len(A.dims), _lib.i64(A.dims), la.encode(), B.ptr,
                len(B.dims), _lib.i64(B.dims), lb.encode(), out.ptr, lc.encode())
     return out
