@@ -136,6 +136,18 @@ def test_factored_atrg3d_matches_oracle(tk, emu, chi, n, block):
     assert "factored" in repr(s)
 
 
+def test_reference_atrg3d_testset_through_factored_step(tk, emu):
+    """The reference's own ATRG_3D testset (test/schemes.jl:365-373): truncrank(12), free energy
+    against f_benchmark3D = -3.507 at rtol 5e-3 -- with maxiter 10 instead of 25 to bound the CPU
+    time (later norms enter with weight 8^-i: they move f by < 1e-9)."""
+    T = tk.classical_ising_3D(tk.Trivial)
+    data = tk.run(tk.ATRG_3D(T, factored=True), tk.truncrank(12), tk.maxiter(10), verbosity=0)
+    f = tk.free_energy(data, tk.ising_βc_3D, scalefactor=8.0)
+    assert abs(f - (-3.507)) <= 5e-3 * 3.507
+    # value of the oracle's full 25-step run (recorded from oracle/tnr_oracle.py, chi = 12)
+    assert abs(f - (-3.517692114222326)) <= 1e-8 * 3.5177
+
+
 def test_factored_atrg3d_chunking_is_exact(tk, emu):
     """TSQR over chunks of the open bond (ragged chunks included) changes nothing."""
     from tnrkit.jl_b200 import atrg3d_factored as af
