@@ -71,6 +71,72 @@ def test_emulated_2d_block_sparse_schemes_match_oracle(tk, emu, name, chi, n, mo
     assert s.T.nnz() < np.prod(s.T.dims)
 
 
+def _model(tk, which):
+    import math
+
+    if which == "sixvertex_u1":
+        return tk.sixvertex(tk.U1Irrep), 1.0, 1.5 * math.log(0.75), 1e-3
+    if which == "clock3_z3":
+        b = 2.0 * math.log(math.sqrt(3.0) + 1.0) / 3.0
+        return tk.classical_clock(tk.ZNIrrep[3], 3, b), b, -4.17924244901635, 1e-3
+    if which == "phi4_z2":
+        return tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-11
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("name,chi,n", [("TRG", 16, 6), ("BTRG", 16, 6), ("HOTRG", 8, 4), ("ATRG", 12, 3)])
+@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2"])
+def test_emulated_block_sparse_u1_and_more_models(tk, emu, name, chi, n, model):
+    """U(1) sectors (six-vertex: charges +-1/2 stored doubled, no modulus), Z3 clock and the
+    Z2 phi^4 tensor with 5-dimensional sectors: block-sparse steps == dense oracle at 1e-10."""
+    T = _model(tk, model)[0]
+    s = getattr(tk, name)(T)
+    assert s.sym and s.T.N == T.N
+    got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+    ref = np.array(o.run(getattr(o, name)(np.asarray(T)), chi, n))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+    assert s.T.nnz() < np.prod(s.T.dims)
+    if model == "sixvertex_u1":
+        assert "U1" in repr(s.T)
+        # U(1): the charges on the coarse legs grow with the bond dimension (no wrap-around)
+        assert max(abs(q) for q in s.T.legs[0].charges) > 1
+        for key in s.T.blocks:
+            assert sum(l.sign * q for l, q in zip(s.T.legs, key)) == 0
+
+
+@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2"])
+def test_emulated_models_testset_block_sparse(tk, emu, model):
+    """test/models.jl:40-46 on the symmetric tensors, block-sparse: TRG, truncrank(16), maxiter(25)."""
+    T, beta, answer, tol = _model(tk, model)
+    data = tk.run(tk.TRG(T), tk.truncrank(16), tk.maxiter(25), verbosity=0)
+    f = tk.free_energy(data, beta)
+    assert abs((f - answer) / answer) < tol
+
+
+def test_u1_tensor_bookkeeping(tk, emu):
+    """SymTensor with N = 0: conservation without a modulus, coupled sectors keyed by the sum."""
+    legs = [tk.Leg({-1: 2, 0: 1, 2: 3}, +1), tk.Leg({-2: 1, 1: 2}, +1), tk.Leg({-1: 2, 0: 2, 3: 1}, -1)]
+    rng = np.random.default_rng(9)
+    dims = tuple(l.total for l in legs)
+    a = rng.standard_normal(dims)
+    q = [np.concatenate([[c] * l.dims[c] for c in l.charges]) for l in legs]
+    for idx in itertools.product(*[range(d) for d in dims]):
+        if sum(l.sign * q[i][j] for i, (l, j) in enumerate(zip(legs, idx))) != 0:
+            a[idx] = 0.0
+    A = tk.SymTensor.from_dense(a, 0, legs)
+    assert set(A.blocks) == {(-1, 1, 0), (2, -2, 0), (2, 1, 3)}
+    assert all(sum(l.sign * c for l, c in zip(legs, k)) == 0 for k in A.blocks)
+    assert np.array_equal(A.to_dense(), a)
+    U, S, V, _ = tk.sym_svd_trunc(A, 2, 100)
+    sref = np.linalg.svd(a.reshape(dims[0] * dims[1], dims[2]), compute_uv=False)
+    got = np.sort(np.concatenate([s.to_numpy() for s in S.values()]))[::-1]
+    assert np.abs(got - sref[:len(got)]).max() <= 1e-12 * sref[0]
+    back = tk.sym_contract(U.scale_leg(2, S), "abk", V, "kc", "abc")
+    assert np.abs(back.to_dense() - a).max() <= 1e-12
+    with pytest.raises(ValueError):
+        tk.SymTensor(1, legs, {})
+
+
 @pytest.mark.parametrize("name,chi,n", [("HOTRG_3D", 4, 3), ("HOTRG_3D", 6, 2), ("ATRG_3D", 4, 3),
                                         ("ATRG_3D", 6, 2)])
 def test_emulated_3d_block_sparse_schemes_match_oracle(tk, emu, name, chi, n):

@@ -8,7 +8,13 @@ test/schemes.jl:141    ATRG  chi=24 it=25  rtol 3e-6 (scalefactor 4)
 test/schemes.jl:360    ATRG_3D  chi=12 it=25 rtol 5e-3 vs -3.507 (scalefactor 8)
 test/schemes.jl:370    HOTRG_3D chi=8  it=25 rtol 1e-3 vs -3.507
 (all of them on the Z2-symmetric model; the dense charge-basis tensor reproduces it.)
+test/models.jl:5-26,40-46  TRG chi=16 it=25, rtol 1e-3, one golden free energy per model: clock
+                       (q = 3, 4; Trivial, ZN), six-vertex (Trivial, U1), real phi^4 (Trivial, Z2)
+                       -- the phi^4 values were recorded from the reference itself and are
+                       reproduced to 1e-12 by oracle TRG + host model constructors.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -53,6 +59,35 @@ def test_models_potts_3state():
     # test/models.jl:16: TRG chi=16 it=25 on classical_potts(Trivial, 3): -4.119552029995684, rtol 1e-3
     d = o.run(o.TRG(o.classical_potts(3)), 16, 25)
     assert rel(o.free_energy(d, o.potts_bc(3)), -4.119552029995684) < 1e-3
+
+
+_SQ3 = 2.0 * math.log(math.sqrt(3.0) + 1.0) / 3.0
+_SQ2 = math.log(math.sqrt(2.0) + 1.0)
+MODEL_GOLDEN = [   # (name, constructor(tk), beta, reference value, tolerance)   test/models.jl:5-26
+    ("clock3", lambda tk: tk.classical_clock(tk.Trivial, 3, _SQ3), _SQ3, -4.17924244901635, 1e-3),
+    ("clock3_Z3", lambda tk: tk.classical_clock(tk.ZNIrrep[3], 3, _SQ3), _SQ3, -4.17924244901635, 1e-3),
+    ("clock4", lambda tk: tk.classical_clock(tk.Trivial, 4, _SQ2), _SQ2, 2 * o.f_onsager, 1e-3),
+    ("clock4_Z4", lambda tk: tk.classical_clock(tk.ZNIrrep[4], 4, _SQ2), _SQ2, 2 * o.f_onsager, 1e-3),
+    ("sixvertex", lambda tk: tk.sixvertex(tk.Trivial), 1.0, 1.5 * math.log(0.75), 1e-3),
+    ("sixvertex_U1", lambda tk: tk.sixvertex(tk.U1Irrep), 1.0, 1.5 * math.log(0.75), 1e-3),
+    # "This is an approximation!" values = the reference's own output: reproduced to 1e-12
+    ("phi4_real", lambda tk: tk.phi4_real(tk.Trivial, 10, -1.0, 1.0), -1.0, 0.4241912271276211, 1e-12),
+    ("phi4_real_Z2", lambda tk: tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-12),
+]
+
+
+@pytest.mark.parametrize("name,make,beta,answer,tol", MODEL_GOLDEN, ids=[m[0] for m in MODEL_GOLDEN])
+def test_models_golden_free_energies(tk, name, make, beta, answer, tol):
+    """test/models.jl:40-46: `TRG(model)`, truncrank(16), maxiter(25), free_energy(data, temp)."""
+    T = make(tk)
+    d = o.run(o.TRG(np.asarray(T)), 16, 25)
+    assert rel(o.free_energy(d, beta), answer) < tol
+    if getattr(T, "charges", None) is not None:      # symmetric variants really are symmetric
+        q = [np.asarray(c) for c in T.charges]
+        tot = sum(s * q[i].reshape([-1 if j == i else 1 for j in range(4)])
+                  for i, s in enumerate(T.signs))
+        forbidden = (tot % T.N != 0) if T.N else (tot != 0)
+        assert np.abs(np.asarray(T)[forbidden]).max() <= 1e-13 * np.abs(np.asarray(T)).max()
 
 
 def test_free_energy_and_driver_semantics():

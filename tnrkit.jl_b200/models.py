@@ -14,10 +14,11 @@ import numpy as np
 
 
 class ChargedArray(np.ndarray):
-    """Host tensor in the charge basis of a Z_N symmetry: `charges[leg][i]` is the irrep label
-    of index i of that leg, `signs[leg]` = +1 (codomain) / -1 (domain), negated for a dual space,
-    and entries are nonzero only where sum_leg sign*charge = 0 mod N -- the information a TensorKit
-    `TensorMap{Float64, Vect[ZNIrrep{N}]}` carries in its spaces."""
+    """Host tensor in the charge basis of a Z_N symmetry (or U(1): N = 0, no modulus):
+    `charges[leg][i]` is the irrep label of index i of that leg, `signs[leg]` = +1 (codomain) /
+    -1 (domain), negated for a dual space, and entries are nonzero only where
+    sum_leg sign*charge = 0 mod N -- the information a TensorKit
+    `TensorMap{Float64, Vect[ZNIrrep{N}]}` (`Vect[U1Irrep]`) carries in its spaces."""
 
     @classmethod
     def wrap(cls, arr, N, charges, signs):
@@ -41,6 +42,11 @@ class Trivial:
 
 class Z2Irrep:
     """Z2 symmetry labels (TensorKitSectors.Z2Irrep)."""
+
+
+class U1Irrep:
+    """U(1) symmetry labels (TensorKitSectors.U1Irrep).  Charges are stored as integers; models
+    with half-integer labels (six-vertex: +-1/2) store twice the charge."""
 
 
 class ZNIrrep:
@@ -162,3 +168,102 @@ def classical_potts(*args):
         return ChargedArray.wrap(np.ascontiguousarray(Ud.real), q, [tuple(range(q))] * 4,
                                  (1, 1, -1, -1))
     raise TypeError(f"classical_potts: unsupported symmetry {sym}")
+
+
+def clock_tensor(q, beta):
+    """src/models/clock.jl:1-12"""
+    A = np.zeros((q,) * 4)
+    clock = lambda i, j: -math.cos(2.0 * math.pi / q * (i - j))  # noqa: E731
+    for i, j, k, l in np.ndindex(q, q, q, q):
+        E = clock(i, j) + clock(j, l) + clock(l, k) + clock(k, i)
+        A[i, j, k, l] = math.exp(-beta * E)
+    return A
+
+
+def classical_clock(*args):
+    """classical_clock([symmetry], q, beta)  -- src/models/clock.jl:26-50.  `Trivial` and
+    `ZNIrrep[q]`; the reference's default, the non-abelian `DNIrrep{q}`, is outside the hot path
+    (no fusion-tree recoupling on the device), so the default here is `ZNIrrep[q]`."""
+    sym, rest = _split(args, None)
+    q, beta = int(rest[0]), float(rest[1])
+    if sym is None:
+        sym = ZNIrrep[q]
+    A = clock_tensor(q, beta)
+    if sym is Trivial:
+        return A
+    if isinstance(sym, type) and issubclass(sym, ZNIrrep):
+        if sym.N != q:
+            raise AssertionError("number of irreps must match the number of states")
+        U = np.exp(2j * math.pi / q * np.outer(np.arange(q), np.arange(q))) / math.sqrt(q)
+        # Anew[-1 -2;-3 -4] := A[1 2;3 4] U[4;-4] conj(U[1;-1]) U[3;-3] conj(U[2;-2])   (clock.jl:44)
+        Anew = np.einsum("ijkl,ia,jb,kc,ld->abcd", A, U.conj(), U.conj(), U, U)
+        return ChargedArray.wrap(np.ascontiguousarray(Anew.real), q, [tuple(range(q))] * 4,
+                                 (1, 1, -1, -1))
+    raise TypeError(f"classical_clock: unsupported symmetry {sym}")
+
+
+def sixvertex(*args, a=1.0, b=1.0, c=1.0):
+    """sixvertex([symmetry]; a, b, c)  -- src/models/sixvertex.jl:28-48.  `Trivial` and `U1Irrep`
+    (the reference's default `CU1Irrep` is non-abelian: outside the hot path; default here U1)."""
+    sym, _ = _split(args, U1Irrep)
+    if sym is Trivial:
+        d = np.array([[a, 0, 0, 0], [0, c, b, 0], [0, b, c, 0], [0, 0, 0, a]], dtype=float)
+        # TensorMap(d, C^2 (x) C^2, C^2 (x) C^2): row = i + 2 j, column = k + 2 l (column major)
+        return np.ascontiguousarray(d.reshape((2, 2, 2, 2), order="F"))
+    if sym is U1Irrep:
+        # pspace = U1Space(-1/2 => 1, 1/2 => 1): index 0 <-> charge -1/2, index 1 <-> +1/2;
+        # block(0) = [b c; c b] on {(-,+), (+,-)}, block(+-1) = [a]
+        t = np.zeros((2, 2, 2, 2))
+        t[0, 0, 0, 0] = t[1, 1, 1, 1] = a
+        t[0, 1, 0, 1] = t[1, 0, 1, 0] = b
+        t[0, 1, 1, 0] = t[1, 0, 0, 1] = c
+        return ChargedArray.wrap(t, 0, [(-1, 1)] * 4, (1, 1, -1, -1))   # charges doubled
+    raise TypeError(f"sixvertex: unsupported symmetry {sym}")
+
+
+def _f_real(p1, p2, mu0, lam, h=0.0):
+    """src/models/phi4_real.jl:1-8"""
+    return math.exp(-0.5 * (p1 - p2) ** 2 - mu0 / 8.0 * (p1 ** 2 + p2 ** 2)
+                    - lam / 16.0 * (p1 ** 4 + p2 ** 4) + h / 4.0 * (p1 + p2))
+
+
+def phi4_real(*args):
+    """phi4_real([symmetry], K, mu0, lam, [h])  -- src/models/phi4_real.jl:75-139.
+    Trivial: Gauss-Hermite quadrature with K points; Z2Irrep (default): Taylor expansion of the
+    hopping term, K/2 even + K/2 odd states per leg (h must be 0)."""
+    sym, rest = _split(args, Z2Irrep)
+    K, mu0, lam = int(rest[0]), float(rest[1]), float(rest[2])
+    h = float(rest[3]) if len(rest) > 3 else 0.0
+    if sym is Trivial:
+        ys, ws = np.polynomial.hermite.hermgauss(K)
+        f = np.array([[_f_real(ys[i], ys[j], mu0, lam, h) for j in range(K)] for i in range(K)])
+        U, S, V = np.linalg.svd(f)
+        rs = np.sqrt(S)
+        w = ws * np.exp(ys ** 2)
+        # T[i j k l] = sum_p sqrt(S_i S_j S_k S_l) w_p U[p,i] U[p,j] V[k,p] V[l,p]
+        return np.einsum("p,pi,pj,kp,lp->ijkl", w, U * rs, U * rs, rs[:, None] * V,
+                         rs[:, None] * V, optimize=True)
+    if sym is Z2Irrep:
+        if h != 0.0:
+            raise AssertionError("External magnetic field is not compatible with Z2 symmetry")
+        if K % 2 != 0:
+            raise ValueError("K must be even to split into even/odd groups")
+        from scipy.integrate import quad
+
+        a_, b_ = (4.0 + mu0) / 2.0, lam / 4.0
+        moments = np.zeros(4 * (K - 1) + 1)
+        for n in range(0, 4 * (K - 1) + 1, 2):
+            moments[n] = quad(lambda x, n=n: math.exp(-a_ * x * x - b_ * x ** 4) * x ** n,
+                              -np.inf, np.inf, epsabs=0.0, epsrel=1e-12, limit=400)[0]
+        logfact = np.array([math.lgamma(s + 1.0) for s in range(K)])
+        t = np.zeros((K,) * 4)
+        for s in np.ndindex(K, K, K, K):
+            n = sum(s)
+            if n % 2:
+                continue
+            t[s] = moments[n] / math.exp(0.5 * sum(logfact[x] for x in s))
+        perm = list(range(0, K, 2)) + list(range(1, K, 2))     # evens, then odds
+        t = t[np.ix_(perm, perm, perm, perm)]
+        ch = (0,) * (K // 2) + (1,) * (K // 2)
+        return ChargedArray.wrap(np.ascontiguousarray(t), 2, [ch] * 4, (1, 1, -1, -1))
+    raise TypeError(f"phi4_real: unsupported symmetry {sym}")

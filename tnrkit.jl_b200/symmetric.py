@@ -1,4 +1,5 @@
-"""Block-sparse tensors with an abelian Z_N symmetry (TensorKit `Z2Irrep`, `ZNIrrep{N}`).
+"""Block-sparse tensors with an abelian symmetry: Z_N (TensorKit `Z2Irrep`, `ZNIrrep{N}`) or
+U(1) (`U1Irrep`; `N = 0`: integer charges without a modulus, half-integer labels stored doubled).
 
 The host keeps the sector / block structure (which charge tuples are allowed, block shapes,
 offsets); the data of every block lives in device memory.  This mirrors how TensorKit stores
@@ -12,9 +13,9 @@ TRG / BTRG `step!` bodies need are
                    (`tnr_topk_select` over the concatenated spectra);
   * permute      = per-block index permutation (`tnr_permute`).
 
-Conservation law: a block with charges (q_1..q_r) is present iff sum_i sign_i * q_i = 0 mod N,
-sign = +1 for codomain-like legs and -1 for domain-like legs.  All fusion / braiding symbols of
-Z_N are 1, so no recoupling coefficients appear.
+Conservation law: a block with charges (q_1..q_r) is present iff sum_i sign_i * q_i = 0 mod N
+(= 0 exactly for U(1)), sign = +1 for codomain-like legs and -1 for domain-like legs.  All
+fusion / braiding symbols of Z_N and U(1) are 1, so no recoupling coefficients appear.
 """
 from __future__ import annotations
 
@@ -62,13 +63,20 @@ def _colmajor_strides(dims):
 
 
 class SymTensor:
-    """Z_N block-sparse tensor: `blocks[(q_1..q_r)]` is a dense DeviceTensor."""
+    """Z_N (N >= 2) or U(1) (N = 0) block-sparse tensor: `blocks[(q_1..q_r)]` is a dense
+    DeviceTensor."""
 
     def __init__(self, N, legs, blocks, ctx=None):
         self.N = int(N)
+        if self.N == 1 or self.N < 0:
+            raise ValueError("SymTensor: N must be 0 (U(1)) or >= 2 (Z_N)")
         self.legs = list(legs)
         self.blocks = dict(blocks)
         self._ctx = ctx
+
+    def _fuse(self, c: int) -> int:
+        """Coupled charge: reduced mod N for Z_N, as is for U(1)."""
+        return c % self.N if self.N else c
 
     @property
     def ctx(self):
@@ -79,7 +87,7 @@ class SymTensor:
 
     # ---- structure ---------------------------------------------------------
     def allowed(self, key):
-        return sum(l.sign * q for l, q in zip(self.legs, key)) % self.N == 0
+        return self._fuse(sum(l.sign * q for l, q in zip(self.legs, key))) == 0
 
     def keys(self):
         for key in itertools.product(*[l.charges for l in reversed(self.legs)]):
@@ -112,7 +120,8 @@ class SymTensor:
             mask[sl] = True
         viol = np.abs(arr[~mask]).max() if (~mask).any() else 0.0
         if viol > tol * max(1.0, np.abs(arr).max()):
-            raise ValueError(f"tensor is not Z{N} symmetric (forbidden entries up to {viol:.2e})")
+            raise ValueError(f"tensor is not {'Z%d' % N if N else 'U(1)'} symmetric "
+                             f"(forbidden entries up to {viol:.2e})")
         return t
 
     def to_dense(self):
@@ -136,9 +145,9 @@ class SymTensor:
         legs = [self.legs[i] for i in which]
         for key in itertools.product(*[l.charges for l in reversed(legs)]):
             key = tuple(reversed(key))
-            c = sum(l.sign * q for l, q in zip(legs, key)) % self.N
+            c = self._fuse(sum(l.sign * q for l, q in zip(legs, key)))
             if negate:
-                c = (-c) % self.N
+                c = self._fuse(-c)
             lst = out.setdefault(c, [])
             off = lst[-1][1] + lst[-1][2] if lst else 0
             lst.append((key, off, math.prod(l.dims[q] for l, q in zip(legs, key))))
@@ -163,7 +172,7 @@ class SymTensor:
         for key, blk in self.blocks.items():
             rk = tuple(key[i] for i in rows)
             ck = tuple(key[i] for i in cols)
-            c = sum(self.legs[i].sign * key[i] for i in rows) % self.N
+            c = self._fuse(sum(self.legs[i].sign * key[i] for i in rows))
             M = mats[c]
             roff, _ = rlook[c][rk]
             coff, _ = clook[c][ck]
@@ -205,7 +214,8 @@ class SymTensor:
         return self
 
     def __repr__(self):
-        return f"SymTensor(Z{self.N}, dims={self.dims}, blocks={len(self.blocks)})"
+        name = f"Z{self.N}" if self.N else "U1"
+        return f"SymTensor({name}, dims={self.dims}, blocks={len(self.blocks)})"
 
 
 # ------------------------------------------------------------------------------------
@@ -634,7 +644,8 @@ def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> Sym
     d = T.dims
     bx, by = Ux.legs[2], Uy.legs[2]
     out_legs = [T.legs[0], T.legs[1], by, bx, by.flipped(), bx.flipped()]
-    base = d[0] * d[2] * d[4] * d[1] * d[2] * d[4] / max(1, T.N)   # R per unit |F||D|
+    nsect = T.N if T.N else max(1, len(bx.charges))
+    base = d[0] * d[2] * d[4] * d[1] * d[2] * d[4] / max(1, nsect)   # R per unit |F||D|
     c = int(math.sqrt(max(1.0, max_elems / max(1.0, base))))
     if c >= max(bx.dims.values()):
         chunks = [None]
