@@ -404,12 +404,9 @@ class HOTRG_3D(_Sym3D, TNRScheme):
                  max_chunk_elems=1 << 29):
         self.group = group
         self.max_chunk_elems = int(max_chunk_elems)
-        if self._init_sym3d(T, symmetric, ctx):
-            if shard:
-                raise NotImplementedError("bond sharding of the block-sparse HOTRG_3D step")
-            self.shard = False
-            return
-        TNRScheme.__init__(self, T, ctx)
+        is_sym = self._init_sym3d(T, symmetric, ctx)
+        if not is_sym:
+            TNRScheme.__init__(self, T, ctx)
         if shard is None:
             try:
                 import torch.distributed as dist
@@ -419,6 +416,8 @@ class HOTRG_3D(_Sym3D, TNRScheme):
             except Exception:
                 shard = False
         self.shard = bool(shard)
+        if is_sym:
+            return
         # peer_scatter: publish every T' slab to all ranks with NVLink stores from the producing
         # kernel (torch symmetric memory provides the peer-mapped buffers) instead of an NCCL
         # all-gather afterwards.  None = try, fall back to NCCL when symmetric memory is absent.
@@ -491,7 +490,12 @@ class HOTRG_3D(_Sym3D, TNRScheme):
         if self.sym:
             from .symmetric import hotrg3d_step_sym
 
-            self.T = hotrg3d_step_sym(self.T, chi, self.max_chunk_elems)
+            sh = None
+            if self.shard:
+                import torch.distributed as dist
+
+                sh = (dist.get_rank(self.group), dist.get_world_size(self.group), self.group)
+            self.T = hotrg3d_step_sym(self.T, chi, self.max_chunk_elems, sh)
             return self
         for _ in range(3):
             self._substep(chi)

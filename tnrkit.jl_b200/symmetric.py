@@ -539,16 +539,23 @@ NO_TRUNCATION = 10 ** 9   # truncrank large enough to keep every value (left_ort
 LAST_PLAN = {}            # how the latest chunked step was split (for inspection / tests)
 
 
-def sym_zeros(N, legs, ctx) -> SymTensor:
-    """All symmetry-allowed blocks, zero-initialised on the device."""
+def sym_zeros(N, legs, ctx, flat=False):
+    """All symmetry-allowed blocks, zero-initialised on the device.  `flat=True`: the blocks are
+    views of ONE buffer, which is returned as well (one collective moves the whole tensor)."""
     import torch
 
     t = SymTensor(N, legs, {}, ctx)
-    for key in t.keys():
-        bd = t.block_dims(key)
-        buf = torch.zeros(max(1, math.prod(bd)), dtype=torch.float64, device=t.ctx.torch_device)
-        t.blocks[key] = DeviceTensor(buf, bd, None, t.ctx)
-    return t
+    keys = list(t.keys())
+    sizes = [max(1, math.prod(t.block_dims(k))) for k in keys]
+    if flat:
+        whole = torch.zeros(max(1, sum(sizes)), dtype=torch.float64, device=t.ctx.torch_device)
+    off = 0
+    for key, n in zip(keys, sizes):
+        buf = whole[off: off + n] if flat else \
+            torch.zeros(n, dtype=torch.float64, device=t.ctx.torch_device)
+        off += n
+        t.blocks[key] = DeviceTensor(buf, t.block_dims(key), None, t.ctx)
+    return (t, whole) if flat else t
 
 
 def leg_chunks(leg: Leg, size: int):
@@ -626,13 +633,18 @@ def _hotrg3d_xproj_sym(A1: SymTensor, A2: SymTensor, chi: int) -> SymTensor:
     return U2 if e > e2 else U
 
 
-def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> SymTensor:
+def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29, shard=None) -> SymTensor:
     """_step!(::HOTRG_3D) on a Z_N tensor -- src/schemes/hotrg3d.jl:102-129.
 
     The chi^8 intermediate of the pairwise contraction order is never formed beyond `max_elems`
     doubles: the two new open x-bonds (-4 and -6) are chunked, every (F, D) pair of chunks is
     contracted on its own and scattered into the index ranges [.., D, .., F] of the output
-    blocks (same chunking as the dense engine, csrc/schemes.cu: hotrg3d_substep)."""
+    blocks (same chunking as the dense engine, csrc/schemes.cu: hotrg3d_substep).
+
+    `shard = (rank, world, group)`: the F chunks of the open x-bond -6 are dealt round-robin to
+    the ranks (projectors and P_D are recomputed on every rank, as in the dense sharded step);
+    every rank fills its index ranges of the zero-initialised output blocks, which live in one
+    flat buffer, and one all-reduce (sum of disjoint supports: exact) replicates T'."""
     Ux = _hotrg3d_xproj_sym(T, T, chi)
     yperm = (0, 1, 3, 2, 5, 4)   # ((1,2),(4,3,6,5)), hotrg3d.jl:109
     Ty = T.permute(yperm)
@@ -647,7 +659,13 @@ def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> Sym
     nsect = T.N if T.N else max(1, len(bx.charges))
     base = d[0] * d[2] * d[4] * d[1] * d[2] * d[4] / max(1, nsect)   # R per unit |F||D|
     c = int(math.sqrt(max(1.0, max_elems / max(1.0, base))))
-    if c >= max(bx.dims.values()):
+    rank, world, group = shard if shard is not None else (0, 1, None)
+    if world > 1:
+        # at least `world` chunks: shrink the chunk width until the x-bond splits that far
+        c = min(c, max(bx.dims.values()))
+        while c > 1 and len(leg_chunks(bx, c)) < world:
+            c -= 1
+    if world == 1 and c >= max(bx.dims.values()):
         chunks = [None]
     else:
         chunks = leg_chunks(bx, max(1, c))
@@ -657,10 +675,18 @@ def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> Sym
         return sym_contract(T, "zbstuw", u, "qtd", "zbsuwqd")      # [z b y2' y2 x2 x1' d]
 
     cache = T.nnz() * bx.total <= 4 * max_elems     # all P_D together: nnz(T) * |x-bond| doubles
-    LAST_PLAN["hotrg3d"] = {"chunks": len(chunks), "chunk_size": c, "cached_P": bool(cache)}
+    mine = list(range(rank, len(chunks), world))
+    LAST_PLAN["hotrg3d"] = {"chunks": len(chunks), "chunk_size": c, "cached_P": bool(cache),
+                            "world": world, "my_F_chunks": len(mine)}
     P = [Pd(D) for D in chunks] if cache else None
-    out = None if chunks == [None] else sym_zeros(T.N, out_legs, T.ctx)
-    for F in chunks:
+    whole = None
+    if chunks == [None]:
+        out = None
+    elif world > 1:
+        out, whole = sym_zeros(T.N, out_legs, T.ctx, flat=True)
+    else:
+        out = sym_zeros(T.N, out_legs, T.ctx)
+    for F in [chunks[i] for i in mine]:
         u = Uxc if F is None else sym_slice(Uxc, 2, F)
         Q = sym_contract(T, "azpqrx", u, "xwf", "azpqrwf")         # [a z y1' x1' y1 x2 f]
         for j, D in enumerate(chunks):
@@ -670,13 +696,17 @@ def hotrg3d_substep_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> Sym
             if out is None:
                 return R
             sym_scatter(out, R, {3: D, 5: F})
+    if whole is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(whole, op=dist.ReduceOp.SUM, group=group)
     return out
 
 
-def hotrg3d_step_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29) -> SymTensor:
+def hotrg3d_step_sym(T: SymTensor, chi: int, max_elems: int = 1 << 29, shard=None) -> SymTensor:
     """step!(::HOTRG_3D) on a Z_N tensor -- src/schemes/hotrg3d.jl:131-139."""
     for _ in range(3):
-        T = hotrg3d_substep_sym(T, chi, max_elems).permute((5, 3, 1, 2, 0, 4))  # ((6,4),(2,3,1,5))
+        T = hotrg3d_substep_sym(T, chi, max_elems, shard).permute((5, 3, 1, 2, 0, 4))  # ((6,4),(2,3,1,5))
     return T
 
 
