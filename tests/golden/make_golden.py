@@ -23,6 +23,16 @@ T3 = o.classical_ising_3D()
 out["HOTRG_3D_ising_trivial_chi6_it4"] = o.run(o.HOTRG_3D(T3), 6, 4)
 out["HOTRG_3D_ising_trivial_chi8_it3"] = o.run(o.HOTRG_3D(T3), 8, 3)
 out["ATRG_3D_ising_z2_chi6_it4"] = o.run(o.ATRG_3D(o.classical_ising_3D_z2basis()), 6, 4)
+# ATRG_3D at the reference's testset size (test/schemes.jl:365-373); 6 steps: from step 8 on the
+# flow at chi = 12 amplifies 1e-15 perturbations of the input beyond 1e-10 (checked by perturbing
+# the oracle's input), so later norms are not a parity target for any implementation
+out["ATRG_3D_ising_trivial_chi12_it6"] = o.run(o.ATRG_3D(T3), 12, 6)
+# keep vectors that are already committed bit-for-bit (LAPACK/BLAS builds differ in the last bit)
+path = os.path.join(HERE, "oracle_norms.json")
+if os.path.exists(path):
+    with open(path) as f:
+        old = json.load(f)
+    out.update({k: v for k, v in old.items() if k in out})
 with open(os.path.join(HERE, "oracle_norms.json"), "w") as f:
     json.dump(out, f, indent=1)
 print({k: len(v) for k, v in out.items()})

@@ -99,6 +99,22 @@ def test_svd_topk_factored_matches_dense_svd(tk, emu, d, block):
     assert np.abs(approx - (u[:, :chi] * s[:chi]) @ vh[:chi]).max() <= 1e-10 * s[0]
 
 
+def test_svd_topk_factored_uncertified_iteration_falls_back_or_raises(tk, emu):
+    """maxit = 1 cannot certify: small matrices are decomposed densely instead, large ones raise
+    (the result never rests on an uncertified subspace)."""
+    from tnrkit.jl_b200.atrg3d_factored import svd_topk_factored
+
+    rng = np.random.default_rng(4)
+    F, dense = _two_factor(tk, rng, (5,) * 6, 40, decay=0.97)
+    st = {}
+    _, S, _ = svd_topk_factored(F, "bef", "cda", 5, stats=st, block=6, maxit=1)
+    assert st["dense"] and "certify" in st["why"]
+    s = np.linalg.svd(np.transpose(dense, (1, 4, 5, 2, 3, 0)).reshape(125, 125), compute_uv=False)
+    assert np.abs(S.to_numpy() - s[:5]).max() <= 1e-12 * s[0]
+    with pytest.raises(tk.TNRCudaError):
+        svd_topk_factored(F, "bef", "cda", 5, block=6, maxit=1, dense_fallback_elems=100)
+
+
 def test_svd_topk_factored_rank_deficient_operator(tk, emu):
     """rank(A) = 3 < chi = 5: the missing triplets are returned as zeros (they enter every later
     contraction with weight sigma or sqrt(sigma))."""
@@ -146,6 +162,18 @@ def test_reference_atrg3d_testset_through_factored_step(tk, emu):
     assert abs(f - (-3.507)) <= 5e-3 * 3.507
     # value of the oracle's full 25-step run (recorded from oracle/tnr_oracle.py, chi = 12)
     assert abs(f - (-3.517692114222326)) <= 1e-8 * 3.5177
+
+
+def test_factored_atrg3d_matches_committed_golden_chi12(tk, emu):
+    """tests/golden/oracle_norms.json: ATRG_3D at the reference's testset size chi = 12, 6 RG steps
+    (block 76 of 1728 columns, chunked TSQR) -- the vector the device twin compares with too."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_norms.json")))
+    ref = np.array(g["ATRG_3D_ising_trivial_chi12_it6"])
+    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), factored=True, max_chunk_elems=12 ** 5 * 5)
+    got = np.array(tk.run(s, tk.truncrank(12), tk.maxiter(6), verbosity=0))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
 
 
 def test_factored_atrg3d_chunking_is_exact(tk, emu):

@@ -61,6 +61,13 @@ def test_factored_equals_dense_device_step(tk, ctx):
     got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
     assert af.LAST_STATS["chunks"]["AX"] == [3]
     assert np.max(np.abs(got - dense) / np.abs(dense)) <= RTOL
+    # and both against the committed oracle vector (tests/golden/make_golden.py)
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_norms.json")))
+    ref = np.array(g["ATRG_3D_ising_trivial_chi12_it6"])[: n + 1]
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+    assert np.max(np.abs(dense - ref) / np.abs(ref)) <= RTOL
 
 
 def _free_port():
