@@ -46,6 +46,26 @@ LEGS = "abcdef"
 BOND = "i"
 BLOCK = "k"          # label of the block index of the subspace iteration
 LAST_STATS = {}      # filled by the last substep: iteration counts, chunk plan (for tests / bench)
+PROFILE = False      # True: synchronise after every phase of a substep and record its seconds
+
+
+class _Phases:
+    """Wall-clock seconds per phase of a substep (only with PROFILE: it synchronises the stream)."""
+
+    def __init__(self, ctx):
+        import time
+
+        self.ctx, self.t, self.out, self.clock = ctx, None, {}, time.perf_counter
+        if PROFILE:
+            ctx.synchronize()
+            self.t = self.clock()
+
+    def mark(self, name):
+        if self.t is not None:
+            self.ctx.synchronize()
+            now = self.clock()
+            self.out[name] = round(self.out.get(name, 0.0) + now - self.t, 6)
+            self.t = now
 
 
 def _view(t: DeviceTensor, dims) -> DeviceTensor:
@@ -429,11 +449,13 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     TwoFactor with legs in the reference's order [D U; N E S W]."""
     dist, rank, world = _dist(shard, group)
     stats = {"svd": []}
+    ph = _Phases(T.ctx)
     F = T.relabel()
     # U, S, V = svd_trunc(permute(T, ((2,5,6),(3,4,1))))                         atrg3d.jl:35
     st = {}
     fU, fS, fV = svd_topk_factored(F, "bef", "cda", chi, tol=tol, stats=st, block=block)   # [i2 i5 i6 k], [i3 i4 i1 k]
     stats["svd"].append(st)
+    ph.mark("svd_T")
     US = _scale_leg(fU.clone(), 3, fS)        # C = U*S
     SV = _scale_leg(fV.clone(), 3, fS)        # B = S*V
     # M[-1 -2;-3 -4 -5 -6] := B[1 -2;-3 -4] C[-1 1;-5 -6]; as permute(M, ((2,5,6),(3,4,1))) its
@@ -442,6 +464,7 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     st = {}
     gU, gS, gV = svd_topk_factored(M, "bef", "cda", chi, tol=tol, stats=st, block=block)   # [m2 m5 m6 k], [m3 m4 m1 k]
     stats["svd"].append(st)
+    ph.mark("svd_M")
     del M, US, SV
     _scale_leg(gU, 3, gS, 1)                  # X = U*sqrt(S)
     _scale_leg(gV, 3, gS, 1)                  # Y = sqrt(S)*V
@@ -459,13 +482,18 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
                        "width": (width_a, width_b), "world": world}
     R1, R3 = _r_factors(YDc, dist, group)      # left_orth(YD ...)   [r; 5 6], [r; 3 4]
     R2t, R4t = _r_factors(AXc, dist, group)    # right_orth(AX ...)^T
+    ph.mark("r_factors")
     P1, P2 = _projectors(R1, R2t, chi)         # Proj_1 [5 6; k], Proj_2 [k; 5 6]
     P3, P4 = _projectors(R3, R4t, chi)         # Proj_3 [3 4; k], Proj_4 [k; 3 4]
     del R1, R2t, R3, R4t
+    ph.mark("projectors")
     # H[-1 -2;-3 -4] := YD[-1 -2;1 2 3 4] Proj_3[1 2;-3] Proj_1[3 4;-4]           :68
     H, lh = _squeeze(YDc, P3, "cdC", P1, "efD", dist, group)     # [a C D b]
     # G[-1 -2;-3 -4] := AX[-1 -2;1 2 3 4] Proj_4[-3;1 2] Proj_2[-4;3 4]           :69
     G, lg = _squeeze(AXc, P4, "Ccd", P2, "Def", dist, group)     # [b C D a]
+    ph.mark("squeeze_H_G")
+    if ph.out:
+        stats["phase_s"] = ph.out
     # T[-1 -2;-3 -4 -5 -6] := G[1 -2;-5 -6] H[-1 1;-3 -4]                        :71
     ren_h = {"a": "a", "b": BOND, "C": "c", "D": "d"}
     ren_g = {"a": BOND, "b": "b", "C": "e", "D": "f"}

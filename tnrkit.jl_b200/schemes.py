@@ -224,7 +224,7 @@ class ATRG_3D(_Sym3D, TNRScheme):
     DENSE_BYTES_LIMIT = 150e9
 
     def __init__(self, T, ctx=None, symmetric=None, factored=None, shard=None, group=None,
-                 max_chunk_elems=1 << 31, tol=1e-13, block=None):
+                 max_chunk_elems=1 << 30, tol=1e-13, block=None):
         self._F = None
         self.block = block
         self.factored = factored

@@ -24,7 +24,10 @@ ap.add_argument("--chi", type=int, default=48)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dense", action="store_true", help="the dense tnr_atrg3d_step instead")
 ap.add_argument("--block", type=int, default=None)
-ap.add_argument("--max-chunk-elems", type=int, default=1 << 31)
+ap.add_argument("--phases", action="store_true",
+                help="synchronise after every phase of a substep and report its seconds (adds "
+                     "host syncs: use for the breakdown, not for the headline time)")
+ap.add_argument("--max-chunk-elems", type=int, default=1 << 30)
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,6 +40,7 @@ if world > 1:
 import tnrkit.jl_b200 as tk  # noqa: E402
 from tnrkit.jl_b200 import atrg3d_factored as af  # noqa: E402
 
+af.PROFILE = bool(args.phases)
 ctx = tk.default_context()
 T = tk.classical_ising_3D(tk.Trivial)
 if args.dense:
