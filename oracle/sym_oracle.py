@@ -85,7 +85,7 @@ class TRG_sym:
         U, s, V, _, sp2, b2 = sector_svd_trunc(Tp, 2, chi, [ch[p] for p in perm],
                                                [sg[p] for p in perm], N)
         C, D = U * np.sqrt(s), np.sqrt(s)[:, None, None] * V
-        self.T = np.einsum("bpq,asp,src,rqd->abcd", D, B, C, A, optimize=True)
+        self.T = np.einsum("bpq,asp,src,rqd->abcd", D, B, C, A, optimize=o._OPT)
         # new legs: a = bond of B (+, sector c1), b = bond of D (+, c2), c = bond of C (-), d = A (-)
         self.charges = [b1, b2, b2, b1]
         self.signs = [1, 1, -1, -1]

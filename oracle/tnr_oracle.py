@@ -32,6 +32,10 @@ from __future__ import annotations
 import math
 import numpy as np
 
+# einsum path: greedy pairwise contraction WITHOUT numpy's default cap on intermediate size (the cap
+# makes a 4-operand network with input legs larger than chi fall back to one naive loop)
+_OPT = ("greedy", 1 << 40)
+
 # ----------------------------------------------------------------------------
 # constants  (src/models/ising.jl:1-8, src/models/potts.jl:33)
 # ----------------------------------------------------------------------------
@@ -178,7 +182,7 @@ class TRG(Scheme):
         U, s, V, _ = svd_trunc(Tp, 2, chi)
         C, D = U * np.sqrt(s), np.sqrt(s)[:, None, None] * V
         # T[-1 -2; -3 -4] := D[-2; 1 2] * B[-1; 4 1] * C[4 3; -3] * A[3 2; -4]
-        self.T = np.einsum("bpq,asp,src,rqd->abcd", D, B, C, A, optimize=True)
+        self.T = np.einsum("bpq,asp,src,rqd->abcd", D, B, C, A, optimize=_OPT)
 
     def finalize(self):
         n = abs(np.einsum("abba->", self.T))  # T[1 2; 2 1]
@@ -205,7 +209,7 @@ class BTRG(Scheme):
         C, D, S2n = U * Sa, Sa[:, None, None] * V, np.diag(Sb)
         # T := D[-1;4 7] S1[1;7] B[-2;1 3] S2[3;2] C[8 2;-4] S1[8;5] A[6 5;-3] S2[4;6]
         self.T = np.einsum("aqt,it,bik,kj,ujd,uo,poc,qp->abcd",
-                           D, self.S1, B, self.S2, C, self.S1, A, self.S2, optimize=True)
+                           D, self.S1, B, self.S2, C, self.S1, A, self.S2, optimize=_OPT)
         self.S1, self.S2 = S1n, S2n
 
     def finalize(self):
@@ -481,7 +485,7 @@ def hotrg3d_chunk_contract(Qk, Pk):
 def finalize_two_by_two(scheme):
     """src/utility/finalize.jl:17-25 (2x2 unit-cell norm)."""
     T = scheme.T
-    n = abs(np.einsum("gaed,dbfg,cfbh,heac->", T, T, T, T, optimize=True))
+    n = abs(np.einsum("gaed,dbfg,cfbh,heac->", T, T, T, T, optimize=_OPT))
     f = n ** 0.25
     scheme.T = T / f
     return f

@@ -29,6 +29,8 @@ MODELS = {
     # order (near-)degenerate singular values differently (weight 2^-i in f), hence 1e-6 here
     "phi4_real": (lambda tk: tk.phi4_real(tk.Trivial, 10, -1.0, 1.0), -1.0, 0.4241912271276211, 1e-6),
     "phi4_real_z2": (lambda tk: tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-6),
+    "phi4_complex": (lambda tk: tk.phi4_complex(tk.Trivial, 6, -1.0, 1.0), -1.0, 0.7583605364656325, 1e-6),
+    "phi4_complex_u1": (lambda tk: tk.phi4_complex(6, -1.0, 1.0), -1.0, 0.7673189874157453, 1e-6),
 }
 
 

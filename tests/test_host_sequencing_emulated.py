@@ -81,6 +81,8 @@ def _model(tk, which):
         return tk.classical_clock(tk.ZNIrrep[3], 3, b), b, -4.17924244901635, 1e-3
     if which == "phi4_z2":
         return tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-11
+    if which == "phi4_complex_u1":     # 36-dimensional legs, 11 U(1) sectors, 891 blocks
+        return tk.phi4_complex(6, -1.0, 1.0), -1.0, 0.7673189874157453, 1e-10
     raise KeyError(which)
 
 
@@ -104,7 +106,7 @@ def test_emulated_block_sparse_u1_and_more_models(tk, emu, name, chi, n, model):
             assert sum(l.sign * q for l, q in zip(s.T.legs, key)) == 0
 
 
-@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2"])
+@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2", "phi4_complex_u1"])
 def test_emulated_models_testset_block_sparse(tk, emu, model):
     """test/models.jl:40-46 on the symmetric tensors, block-sparse: TRG, truncrank(16), maxiter(25)."""
     T, beta, answer, tol = _model(tk, model)

@@ -9,7 +9,8 @@ test/schemes.jl:360    ATRG_3D  chi=12 it=25 rtol 5e-3 vs -3.507 (scalefactor 8)
 test/schemes.jl:370    HOTRG_3D chi=8  it=25 rtol 1e-3 vs -3.507
 (all of them on the Z2-symmetric model; the dense charge-basis tensor reproduces it.)
 test/models.jl:5-26,40-46  TRG chi=16 it=25, rtol 1e-3, one golden free energy per model: clock
-                       (q = 3, 4; Trivial, ZN), six-vertex (Trivial, U1), real phi^4 (Trivial, Z2)
+                       (q = 3, 4; Trivial, ZN), six-vertex (Trivial, U1), real phi^4 (Trivial, Z2),
+                       complex phi^4 (Trivial, U1)
                        -- the phi^4 values were recorded from the reference itself and are
                        reproduced to 1e-12 by oracle TRG + host model constructors.
 """
@@ -73,6 +74,10 @@ MODEL_GOLDEN = [   # (name, constructor(tk), beta, reference value, tolerance)  
     # "This is an approximation!" values = the reference's own output: reproduced to 1e-12
     ("phi4_real", lambda tk: tk.phi4_real(tk.Trivial, 10, -1.0, 1.0), -1.0, 0.4241912271276211, 1e-12),
     ("phi4_real_Z2", lambda tk: tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-12),
+    # complex phi^4, bond dimension 36 (K = 6): also the reference's own output; the U(1) tensor has
+    # 11 charge sectors -5..5.  (Trivial: 2e-10, one near-degenerate cut reacts to summation order)
+    ("phi4_complex", lambda tk: tk.phi4_complex(tk.Trivial, 6, -1.0, 1.0), -1.0, 0.7583605364656325, 1e-8),
+    ("phi4_complex_U1", lambda tk: tk.phi4_complex(6, -1.0, 1.0), -1.0, 0.7673189874157453, 1e-11),
 ]
 
 

@@ -267,3 +267,68 @@ def phi4_real(*args):
         ch = (0,) * (K // 2) + (1,) * (K // 2)
         return ChargedArray.wrap(np.ascontiguousarray(t), 2, [ch] * 4, (1, 1, -1, -1))
     raise TypeError(f"phi4_real: unsupported symmetry {sym}")
+
+
+def _f_complex(r1, c1, r2, c2, mu0, lam):
+    """src/models/phi4_complex.jl:1-7"""
+    return math.exp(-0.5 * ((r1 - r2) ** 2 + (c1 - c2) ** 2)
+                    - mu0 / 8.0 * (r1 ** 2 + c1 ** 2 + r2 ** 2 + c2 ** 2)
+                    - lam / 16.0 * ((r1 ** 2 + c1 ** 2) ** 2 + (r2 ** 2 + c2 ** 2) ** 2))
+
+
+def phi4_complex(*args):
+    """phi4_complex([symmetry], K, mu0, lam)  -- src/models/phi4_complex.jl:152-160, 219-281.
+    Trivial: Gauss-Hermite quadrature in Re/Im (bond dimension K^2); U1Irrep (default): Taylor
+    expansion in phi, phi^* with charges q = a - B, a, B in 0..K-1 (bond dimension K^2, 2K-1
+    sectors).  The Z2 x Z2 variant (product sector) is not built."""
+    sym, rest = _split(args, U1Irrep)
+    K, mu0, lam = int(rest[0]), float(rest[1]), float(rest[2])
+    if sym is Trivial:
+        ys, ws = np.polynomial.hermite.hermgauss(K)
+        N = K * K
+        # fmatrix_complex: index (i-1)K + j  <->  phi = ys[i] + i ys[j]
+        f = np.empty((N, N))
+        for i in range(K):
+            for j in range(K):
+                for k in range(K):
+                    for l in range(K):
+                        f[i * K + j, k * K + l] = _f_complex(ys[i], ys[j], ys[k], ys[l], mu0, lam)
+        w = np.array([ws[a] * ws[b] * math.exp(ys[a] ** 2 + ys[b] ** 2)
+                      for a in range(K) for b in range(K)])
+        U, S, V = np.linalg.svd(f)
+        rs = np.sqrt(S)
+        full = np.einsum("p,pi,pj,kp,lp->ijkl", w, U * rs, U * rs, rs[:, None] * V, rs[:, None] * V,
+                         optimize=True)
+        # phi4_complex_tensor computes the entry of the sorted index tuple and assigns it to all
+        # 24 permutations (phi4_complex.jl:117-137)
+        idx = np.sort(np.stack(np.meshgrid(*[np.arange(N)] * 4, indexing="ij"), axis=-1), axis=-1)
+        return np.ascontiguousarray(full[idx[..., 0], idx[..., 1], idx[..., 2], idx[..., 3]])
+    if sym is U1Irrep:
+        if K % 2 != 0:
+            raise ValueError("K must be even")
+        from scipy.integrate import quad
+
+        a_, b_ = 2.0 + mu0 / 2.0, lam / 4.0
+        nmax = 8 * (K - 1) + 1
+        moments = np.zeros(nmax + 1)
+        for n in range(nmax + 1):
+            moments[n] = quad(lambda r, n=n: math.exp(n * math.log(r) - a_ * r * r - b_ * r ** 4)
+                              if r > 0.0 else (1.0 if n == 0 else 0.0),
+                              0.0, np.inf, epsabs=0.0, epsrel=1e-13, limit=400)[0]
+        logfact = np.array([math.lgamma(x + 1.0) for x in range(K)])
+        # basis of W = fuse(V1, V2): states (a, B) with charge q = a - B, ordered by (q, a)
+        states = sorted(((a - B, a, B) for a in range(K) for B in range(K)))
+        ch = tuple(q for q, _, _ in states)
+        N = len(states)
+        pw = np.array([a + B for _, a, B in states])
+        lf = np.array([logfact[a] + logfact[B] for _, a, B in states])
+        q = np.array(ch)
+        sp = pw[:, None, None, None] + pw[None, :, None, None] + pw[None, None, :, None] + pw[None, None, None, :]
+        ld = 0.5 * (math.log(2.0) * sp + lf[:, None, None, None] + lf[None, :, None, None]
+                    + lf[None, None, :, None] + lf[None, None, None, :])
+        ok = (q[:, None, None, None] + q[None, :, None, None]
+              == q[None, None, :, None] + q[None, None, None, :])
+        t = np.where(ok, 2.0 * math.pi * moments[sp + 1] / np.exp(ld), 0.0)
+        assert t.shape == (N,) * 4
+        return ChargedArray.wrap(np.ascontiguousarray(t), 0, [ch] * 4, (1, 1, -1, -1))
+    raise TypeError(f"phi4_complex: unsupported symmetry {sym}")
