@@ -273,4 +273,4 @@ def test_factored_atrg3d_sharded_world2(chi, budget):
         assert res[r][1]["world"] == 2 and len(res[r][1]["AX"]) == 2
     assert res[0][0] == res[1][0]          # replicas stay bit-identical
     if chi == 5:
-        assert res[0][1]["AX"] == [3, 2]   # ragged ownership of the open bond, chunks of width 1
+        assert res[0][1]["AX"] == [3, 2]   # ragged ownership of the open bond (3 + 2), width 1

@@ -72,6 +72,8 @@ def test_shard_range_partitions(tk):
                 assert 0 <= lo <= hi <= n
                 cover += list(range(lo, hi))
             assert cover == list(range(n))
+            sizes = [hi - lo for lo, hi in (tk.shard_range(n, r, world) for r in range(world))]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
 
 
 def test_abi_exports_every_declared_symbol(tk):

@@ -360,10 +360,11 @@ class BTRG(_SymmetricMixin, TNRScheme):
 
 
 def shard_range(n: int, rank: int, world: int):
-    """Contiguous block of the open bond owned by `rank` (equal blocks when world | n)."""
-    per = -(-n // world)
-    lo = min(n, rank * per)
-    return lo, min(n, lo + per)
+    """Contiguous block of the open bond owned by `rank`: equal blocks when world | n, otherwise
+    the first n mod world ranks own one index more (blocks differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def allgather_last_leg(buf, dims, group=None):
