@@ -70,6 +70,25 @@ def test_factored_equals_dense_device_step(tk, ctx):
     assert np.max(np.abs(dense - ref) / np.abs(ref)) <= RTOL
 
 
+@pytest.mark.parametrize("chi", [16, 24])
+def test_full_size_parity_dense_and_factored_device_steps(tk, ctx, chi):
+    """Sizes the dense numpy oracle cannot reach in seconds (chi = 24: 1.5 GB tensors): the DENSE
+    device step (`tnr_atrg3d_step`) and the factored device step against the vector computed on the
+    CPU by the factored step over LAPACK (tests/golden/make_golden_factored.py) -- three
+    implementations (dense/Jacobi/GPU, factored/Jacobi/GPU, factored/LAPACK/CPU) of atrg3d.jl."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "factored_cpu_norms.json")))
+    ref = np.array(g[f"ATRG_3D_ising_trivial_chi{chi}_it3"])
+    T = tk.classical_ising_3D(tk.Trivial)
+    dense = np.array(tk.run(tk.ATRG_3D(T, factored=False), tk.truncrank(chi), tk.maxiter(3),
+                            verbosity=0))
+    assert np.max(np.abs(dense - ref) / np.abs(ref)) <= RTOL
+    fact = np.array(tk.run(tk.ATRG_3D(T, factored=True), tk.truncrank(chi), tk.maxiter(3),
+                           verbosity=0))
+    assert np.max(np.abs(fact - ref) / np.abs(ref)) <= RTOL
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
