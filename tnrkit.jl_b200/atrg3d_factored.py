@@ -184,14 +184,14 @@ class TwoFactor:
 # ---------------------------------------------------------------------------------------
 # truncated SVD of an implicit operator
 # ---------------------------------------------------------------------------------------
-def _residual_norms(Z: DeviceTensor, Ul: DeviceTensor, sig: DeviceTensor, m: int, k: int):
+def _residual_norms(Z: DeviceTensor, Ul: DeviceTensor, sig: DeviceTensor, m: int, k: int,
+                    eye: DeviceTensor):
     """|| Z[:, j] - sig[j] Ul[:, j] ||_2 for j < k (Z = A V, Ul = left vectors), on the device;
-    only the k norms^2 travel to the host."""
+    only the k norms^2 travel to the host.  `eye`: k x k identity (D -= E I through tnr_gemm)."""
     ctx = Z.ctx
     D = DeviceTensor(Z.buf[: m * k].clone(), (m, k), None, ctx)
     E = DeviceTensor(Ul.buf[: m * k].clone(), (m, k), None, ctx)
     _scale_leg(E, 1, sig)
-    eye = DeviceTensor.from_numpy(np.eye(k), None, ctx)
     ctx.call("tnr_gemm", b"N", b"N", m, k, k, -1.0, E.ptr, m, eye.ptr, k, 1.0, D.ptr, m)
     g = contract(D, "mj", D, "ml", "jl").to_numpy()
     return np.sqrt(np.maximum(np.diag(g), 0.0))
@@ -219,6 +219,7 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     k = min(chi, r)
     b = max(2 * k, k + 64) if block is None else max(int(block), k)
     st = stats if stats is not None else {}
+
     def dense_svd(why):
         dense = contract(F.P, F.lp, F.Q, F.lq, rows + cols)
         U, S, Vt, _ = svd_trunc(dense, len(rows), chi)
@@ -233,18 +234,23 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     Z = F.apply(rows, cols, Q)
     best, stalled = math.inf, 0
     Ul = sig = None
+    eyes = {}
     for it in range(1, maxit + 1):
         U, S, _, _ = svd_trunc(_view(Z, (m, Z.dims[-1])), 1, NO_TRUNCATION)       # Z = U S W^T
         s = S.to_numpy()
         keep = int(np.count_nonzero(s > 1e-14 * s[0]))
+        if keep == 0:
+            return dense_svd("zero operator")
         ke = min(k, keep)     # rank(A) < chi: the block spans the whole range, the rest is zero
+        if ke not in eyes:
+            eyes[ke] = DeviceTensor.from_numpy(np.eye(ke), None, ctx)
         U = DeviceTensor(U.buf[: m * keep], rd + (keep,), None, ctx)
         Y = F.apply(cols, rows, U)                                               # A^T U
         Vh, sig, Xt, _ = svd_trunc(_view(Y, (n, keep)), 1, NO_TRUNCATION)        # Y = Vh sig Xt
         Ul = contract(_view(U, (m, keep)), "mj", Xt, "lj", "ml")                 # left vectors
         Q = _view(Vh, cd + (keep,))
         Z = F.apply(rows, cols, Q)                                               # A Vh (next Z)
-        res = _residual_norms(_view(Z, (m, keep)), Ul, sig, m, ke)
+        res = _residual_norms(_view(Z, (m, keep)), Ul, sig, m, ke, eyes[ke])
         smax = float(sig.to_numpy()[0])
         rel = float(res.max()) / smax if smax > 0.0 else 0.0
         if not math.isfinite(rel):
