@@ -176,6 +176,34 @@ def test_factored_atrg3d_matches_committed_golden_chi12(tk, emu):
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
 
 
+@pytest.mark.parametrize("chi,n", [(6, 4), (10, 3)])
+def test_factored_atrg3d_gram_r_factors_match_oracle(tk, emu, chi, n):
+    """rfactor="gram": R factors from the Gram matrices of the two-factor tensors (O(chi^6), no
+    chunk is ever formed for them) -- same norm lists as the oracle's Householder QR at 1e-10."""
+    from tnrkit.jl_b200 import atrg3d_factored as af
+
+    T = tk.classical_ising_3D(tk.Trivial)
+    s = tk.ATRG_3D(T, factored=True, rfactor="gram")
+    got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
+    ref = np.array(o.run(o.ATRG_3D(T), chi, n))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+    assert af.LAST_STATS["rfactor"] == "gram" and "tnr_orth_r" not in emu.calls
+    with pytest.raises(ValueError):
+        tk.ATRG_3D(T, factored=True, rfactor="qr").step(tk.truncrank(4))
+
+
+def test_factored_atrg3d_gram_matches_tsqr_vector_chi16(tk, emu):
+    """chi = 16 (4096 x 4096 matricizations, 256 x 256 Gram matrices): the Gram path against the
+    committed vector of the TSQR path (tests/golden/factored_cpu_norms.json)."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "factored_cpu_norms.json")))
+    ref = np.array(g["ATRG_3D_ising_trivial_chi16_it3"])
+    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), factored=True, rfactor="gram")
+    got = np.array(tk.run(s, tk.truncrank(16), tk.maxiter(3), verbosity=0))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-11
+
+
 def test_factored_atrg3d_chunking_is_exact(tk, emu):
     """TSQR over chunks of the open bond (ragged chunks included) changes nothing."""
     from tnrkit.jl_b200 import atrg3d_factored as af

@@ -408,6 +408,43 @@ def _r_factors(Z: _ChunkedPair, dist, group):
             _view(R_cd, (R_cd.dims[0], d["c"], d["d"])))
 
 
+def _gram_sqrt(G: DeviceTensor, n: int) -> DeviceTensor:
+    """R' = Lambda_+^{1/2} W^T from the eigendecomposition G = W Lambda W^T of a Gram matrix
+    (negative rounding-noise eigenvalues clipped): R'^T R' = G to eps ||G||."""
+    from .tensor import eigh_trunc
+
+    lam, W, _ = eigh_trunc(_view(G, (n, n)), n)          # sorted by |lambda|, W: n x n
+    root = np.sqrt(np.maximum(lam.to_numpy(), 0.0))      # n numbers through the host
+    R = _view(W, (n, n)).permute((1, 0))
+    return _scale_leg(R, 0, DeviceTensor.from_numpy(root, 1, G.ctx))
+
+
+def _r_factors_gram(F: TwoFactor):
+    """(R_ef, R_cd) as in `_r_factors`, from the Gram matrices of the two matricizations, which
+    follow from the factors without ever forming Z = sum_i P Q:
+        G[(e f),(e' f')] = sum_{i i'} PP[.. i .. i'] QQ[.. i .. i']   (O(chi^6) flop),
+    each P/Q self-contraction running over that factor's open legs that are ROWS.  R' is the
+    PSD square root of G in its eigenbasis.  The projectors of atrg3d.jl:58-66 depend on R1, R2
+    only through R1^T R1 and R2 R2^T (their left orthogonal gauge cancels), so this is the same
+    map evaluated on Gram matrices that are exact to eps ||G||; what is lost against the TSQR
+    path is accuracy in directions with sigma < 1e-8 sigma_1, and the top-chi part of R1 R2 sees
+    that only through the sensitivity (s_1 / s_chi)^2 eps -- measured in the tests."""
+    d = {c: F.dim(c) for c in LEGS}
+    out = []
+    for pair in ("ef", "cd"):
+        up = pair.upper()
+        ren = lambda lab: "".join({pair[0]: up[0], pair[1]: up[1], BOND: "I"}.get(c, c) for c in lab)  # noqa: E731
+        keep_p = "".join(c for c in F.lp if c in pair or c == BOND)
+        keep_q = "".join(c for c in F.lq if c in pair or c == BOND)
+        PP = contract(F.P, F.lp, F.P, ren(F.lp), keep_p + ren(keep_p))
+        QQ = contract(F.Q, F.lq, F.Q, ren(F.lq), keep_q + ren(keep_q))
+        G = contract(PP, keep_p + ren(keep_p), QQ, keep_q + ren(keep_q), pair + up)
+        n = d[pair[0]] * d[pair[1]]
+        R = _gram_sqrt(G, n)
+        out.append(_view(R, (n, d[pair[0]], d[pair[1]])))
+    return out[0], out[1]
+
+
 def _projectors(Rl: DeviceTensor, Rrt: DeviceTensor, chi: int):
     """atrg3d.jl:58-66 with Rl = R1 [r; p q] and Rrt = R2^T [r'; p q]:
     temp = Rl Rr,  U S V = svd_trunc(temp),  Pa[p q; k] = Rr V' S^-1/2,  Pb[k; p q] = S^-1/2 U' Rl."""
@@ -450,7 +487,7 @@ def _squeeze(Z: _ChunkedPair, Pcd: DeviceTensor, lcd: str, Pef: DeviceTensor, le
 # ---------------------------------------------------------------------------------------
 def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 28,
                             shard: bool = False, group=None, tol: float = 1e-13,
-                            block: int | None = None) -> TwoFactor:
+                            block: int | None = None, rfactor: str = "tsqr") -> TwoFactor:
     """`_step!(::ATRG_3D)` (atrg3d.jl:34-83) on a TwoFactor; returns the new tensor as a
     TwoFactor with legs in the reference's order [D U; N E S W]."""
     dist, rank, world = _dist(shard, group)
@@ -486,8 +523,15 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     YDc = _ChunkedPair(YD, "b", width_b, rank, world)
     stats["chunks"] = {"AX": [len(p) for p in AXc.plans], "YD": [len(p) for p in YDc.plans],
                        "width": (width_a, width_b), "world": world}
-    R1, R3 = _r_factors(YDc, dist, group)      # left_orth(YD ...)   [r; 5 6], [r; 3 4]
-    R2t, R4t = _r_factors(AXc, dist, group)    # right_orth(AX ...)^T
+    if rfactor == "gram":
+        R1, R3 = _r_factors_gram(YD)
+        R2t, R4t = _r_factors_gram(AX)
+    elif rfactor == "tsqr":
+        R1, R3 = _r_factors(YDc, dist, group)      # left_orth(YD ...)   [r; 5 6], [r; 3 4]
+        R2t, R4t = _r_factors(AXc, dist, group)    # right_orth(AX ...)^T
+    else:
+        raise ValueError(f"rfactor must be 'tsqr' or 'gram', not {rfactor!r}")
+    stats["rfactor"] = rfactor
     ph.mark("r_factors")
     P1, P2 = _projectors(R1, R2t, chi)         # Proj_1 [5 6; k], Proj_2 [k; 5 6]
     P3, P4 = _projectors(R3, R4t, chi)         # Proj_3 [3 4; k], Proj_4 [k; 3 4]

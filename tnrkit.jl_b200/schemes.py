@@ -224,9 +224,10 @@ class ATRG_3D(_Sym3D, TNRScheme):
     DENSE_BYTES_LIMIT = 150e9
 
     def __init__(self, T, ctx=None, symmetric=None, factored=None, shard=None, group=None,
-                 max_chunk_elems=1 << 30, tol=1e-13, block=None):
+                 max_chunk_elems=1 << 30, tol=1e-13, block=None, rfactor="tsqr"):
         self._F = None
         self.block = block
+        self.rfactor = rfactor
         self.factored = factored
         self.group = group
         self.max_chunk_elems = int(max_chunk_elems)
@@ -292,7 +293,7 @@ class ATRG_3D(_Sym3D, TNRScheme):
         self._to_factored()
         self._F = atrg3d_step_factored(self._F, chi, max_chunk_elems=self.max_chunk_elems,
                                        shard=self.shard, group=self.group, tol=self.tol,
-                                       block=self.block)
+                                       block=self.block, rfactor=self.rfactor)
         return self
 
     def finalize(self):

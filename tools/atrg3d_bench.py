@@ -24,6 +24,9 @@ ap.add_argument("--chi", type=int, default=48)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dense", action="store_true", help="the dense tnr_atrg3d_step instead")
 ap.add_argument("--block", type=int, default=None)
+ap.add_argument("--rfactor", choices=("tsqr", "gram"), default="tsqr",
+                help="R factors by chunked TSQR (2 chi^8 flop each) or from the Gram matrices of the "
+                     "factors (chi^6)")
 ap.add_argument("--phases", action="store_true",
                 help="synchronise after every phase of a substep and report its seconds (adds "
                      "host syncs: use for the breakdown, not for the headline time)")
@@ -47,7 +50,7 @@ if args.dense:
     s = tk.ATRG_3D(T, factored=False)
 else:
     s = tk.ATRG_3D(T, factored=True, shard=world > 1, block=args.block,
-                   max_chunk_elems=args.max_chunk_elems)
+                   max_chunk_elems=args.max_chunk_elems, rfactor=args.rfactor)
 trunc = tk.truncrank(args.chi)
 data = [s.finalize()]
 rows = []
@@ -73,7 +76,7 @@ f = tk.free_energy(data, tk.ising_βc_3D, scalefactor=8.0)
 if rank == 0:
     dims = list(s.factors.dims) if s.factors is not None else list(s.T.dims)
     print(json.dumps({"config": "ATRG_3D classical_ising_3D(Trivial)", "chi": args.chi,
-                      "path": "dense" if args.dense else "factored", "n_gpus": world,
+                      "path": "dense" if args.dense else f"factored/{args.rfactor}", "n_gpus": world,
                       "dims": dims, "steps": rows,
                       "steady_s_per_step": min(r["s"] for r in rows[-2:]),
                       "free_energy": f, "rel_err_vs_f_benchmark3D": abs((f + 3.507) / 3.507),
