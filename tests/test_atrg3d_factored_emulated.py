@@ -255,7 +255,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, chi, n, budget, q):
+def _worker(rank, world, port, chi, n, budget, rfactor, q):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -269,7 +269,8 @@ def _worker(rank, world, port, chi, n, budget, q):
     from tnrkit.jl_b200 import _lib, atrg3d_factored as af
 
     _lib._default_ctx = Emu()
-    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=True, max_chunk_elems=budget)
+    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=True, max_chunk_elems=budget,
+                   rfactor=rfactor)
     assert s.factored and s.shard
     got = tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
     q.put((rank, got, dict(af.LAST_STATS["chunks"])))
@@ -277,15 +278,18 @@ def _worker(rank, world, port, chi, n, budget, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("chi,budget", [(4, 1 << 28), (5, 5 ** 5)])   # even split; ragged 3 + 2
-def test_factored_atrg3d_sharded_world2(chi, budget):
+@pytest.mark.parametrize("chi,budget,rfactor", [(4, 1 << 28, "tsqr"),    # even split
+                                                (5, 5 ** 5, "tsqr"),      # ragged 3 + 2, width 1
+                                                (6, 2000, "gram")])       # only H / G are sharded
+def test_factored_atrg3d_sharded_world2(chi, budget, rfactor):
     import torch.multiprocessing as mp
 
     n = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, chi, n, budget, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, chi, n, budget, rfactor, q))
+             for r in range(2)]
     for p in procs:
         p.start()
     res = {r: (got, ch) for r, got, ch in (q.get(timeout=300) for _ in range(2))}
