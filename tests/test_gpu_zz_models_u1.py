@@ -31,6 +31,8 @@ MODELS = {
     "phi4_real_z2": (lambda tk: tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-6),
     "phi4_complex": (lambda tk: tk.phi4_complex(tk.Trivial, 6, -1.0, 1.0), -1.0, 0.7583605364656325, 1e-6),
     "phi4_complex_u1": (lambda tk: tk.phi4_complex(6, -1.0, 1.0), -1.0, 0.7673189874157453, 1e-6),
+    # test/models.jl:19 (commented out there, "approximation"): 13 one-dimensional U(1) sectors
+    "xy_u1": (lambda tk: tk.classical_XY(tk.U1Irrep, 0.89351, 6), 0.89351, -1.0251, 1e-3),
 }
 
 

@@ -83,6 +83,9 @@ def _model(tk, which):
         return tk.phi4_real(10, -1.0, 1.0), -1.0, 0.4232381701937374, 1e-11
     if which == "phi4_complex_u1":     # 36-dimensional legs, 11 U(1) sectors, 891 blocks
         return tk.phi4_complex(6, -1.0, 1.0), -1.0, 0.7673189874157453, 1e-10
+    if which == "xy_u1":               # 13 one-dimensional U(1) sectors -6..6 (test/models.jl:19,
+        # commented out there as "approximation": -1.0251); +-q sectors are exactly degenerate
+        return tk.classical_XY(tk.U1Irrep, 0.89351, 6), 0.89351, -1.0251, 1e-3
     raise KeyError(which)
 
 
@@ -106,7 +109,7 @@ def test_emulated_block_sparse_u1_and_more_models(tk, emu, name, chi, n, model):
             assert sum(l.sign * q for l, q in zip(s.T.legs, key)) == 0
 
 
-@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2", "phi4_complex_u1"])
+@pytest.mark.parametrize("model", ["sixvertex_u1", "clock3_z3", "phi4_z2", "phi4_complex_u1", "xy_u1"])
 def test_emulated_models_testset_block_sparse(tk, emu, model):
     """test/models.jl:40-46 on the symmetric tensors, block-sparse: TRG, truncrank(16), maxiter(25)."""
     T, beta, answer, tol = _model(tk, model)

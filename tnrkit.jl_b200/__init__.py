@@ -7,7 +7,8 @@ interface for that path: scheme constructors, `run!`, `truncrank`, `maxiter`,
 from . import _lib
 from ._lib import Context, TNRCudaError, default_context
 from .free_energy import free_energy
-from .models import (ChargedArray, Trivial, U1Irrep, Z2Irrep, ZNIrrep, classical_clock,
+from .models import (XY_bc, XY_βc, ChargedArray, Trivial, U1Irrep, Z2Irrep, ZNIrrep, classical_XY,
+                     classical_clock,
                      classical_ising, classical_ising_3D, classical_potts, f_onsager, ising_bc,
                      ising_bc_3D, ising_βc, ising_βc_3D, phi4_complex, phi4_real, potts_bc, potts_βc,
                      sixvertex)

@@ -332,3 +332,34 @@ def phi4_complex(*args):
         assert t.shape == (N,) * 4
         return ChargedArray.wrap(np.ascontiguousarray(t), 0, [ch] * 4, (1, 1, -1, -1))
     raise TypeError(f"phi4_complex: unsupported symmetry {sym}")
+
+
+XY_βc = 1.1199   # src/models/XY.jl:15 ("This is an approximation!")
+XY_bc = XY_βc
+
+
+def classical_XY(*args):
+    """classical_XY([U1Irrep], [beta], charge_trunc)  -- src/models/XY.jl:40-55 + algebraic_initialization
+    (:1-12): legs carry the U(1) charges -charge_trunc..charge_trunc (one state each), the fusion
+    tensor m[u; A B] = 1 where u = A + B, bonds weigh charge q with the Bessel function I_q(beta).
+    Only `U1Irrep` (the reference's default `CU1Irrep` = O(2) is non-abelian)."""
+    from scipy.special import iv
+
+    sym, rest = _split(args, U1Irrep)
+    if sym is not U1Irrep:
+        raise TypeError(f"classical_XY: unsupported symmetry {sym}")
+    beta = float(rest[0]) if len(rest) > 1 else XY_βc
+    c = int(rest[-1])
+    q = np.arange(-c, c + 1)
+    n = q.size
+    m = (q[:, None, None] == q[None, :, None] + q[None, None, :]).astype(float)   # m[u; A B]
+    w = iv(q, beta)
+    # T[l u; d r] := m[u;Au Bu] bond[Au;Ad] bond[Bu;Bd] m[Bd;Cu r] m'[l Ad;Du] bond[Du;Dd]
+    #                bond[Cu;Cd] m'[Dd Cd;d]       with m'[x y; z] = m[z; x y]
+    mw = m * w[None, :, None] * w[None, None, :]            # m[u; A B] I_A I_B
+    md = m * w[:, None, None]                               # m[D; l A] I_D
+    mc = m * w[None, :, None]                               # m[B; C r] I_C
+    t = np.einsum("uAB,BCr,DlA,dDC->ludr", mw, mc, md, m, optimize=True)
+    assert t.shape == (n,) * 4
+    return ChargedArray.wrap(np.ascontiguousarray(t), 0, [tuple(int(x) for x in q)] * 4,
+                             (1, 1, -1, -1))
