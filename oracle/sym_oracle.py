@@ -1,4 +1,4 @@
-"""CPU oracle for the block-sparse (abelian Z_N) semantics -- TEST INFRASTRUCTURE ONLY.
+"""CPU oracle for the block-sparse (abelian Z_N, U(1): N = 0) semantics -- TEST INFRASTRUCTURE ONLY.
 
 TensorKit's `svd_trunc(t; trunc = truncrank(chi))` on a `Z2Irrep` / `ZNIrrep{N}` TensorMap
 decomposes every coupled-sector block separately and keeps the chi largest singular values
@@ -27,13 +27,13 @@ def sector_svd_trunc(T, ncod, chi, charges, signs, N):
             sh = [1] * len(shape)
             sh[ax] = shape[ax]
             q = q + signs[leg] * np.asarray(charges[leg]).reshape(sh)
-        q = (-q if negate else q) % N
-        return q.reshape(-1)
+        q = -q if negate else q
+        return (q % N if N else q).reshape(-1)      # N = 0: U(1), no modulus
 
     qr = fused(cod, range(ncod), False)
     qc = fused(dom, range(ncod, T.ndim), True)
     facs, allv = {}, []
-    for c in range(N):
+    for c in sorted(set(qr.tolist()) | set(qc.tolist())):
         r, cidx = np.where(qr == c)[0], np.where(qc == c)[0]
         if len(r) == 0 or len(cidx) == 0:
             continue

@@ -60,3 +60,17 @@ def test_block_sparse_u1_and_more_models_match_oracle(tk, ctx, name, chi, n, mod
     if model == "sixvertex_u1":
         for key in s.T.blocks:      # U(1): exact conservation, no modulus
             assert sum(l.sign * q for l, q in zip(s.T.legs, key)) == 0
+
+
+@pytest.mark.parametrize("chi", [16, 13])
+@pytest.mark.parametrize("model", ["xy_u1", "sixvertex_u1", "phi4_complex_u1", "clock4_z4"])
+def test_block_sparse_trg_equals_sector_oracle_on_device(tk, model, chi):
+    """TensorKit's sector-global truncrank (oracle/sym_oracle.py) on tensors with exactly
+    degenerate sectors, cuts through the multiplets included (chi = 13): gauge-invariant norm
+    lists agree.  1e-10: the north star's tolerance (CPU twin: 1e-12)."""
+    import sym_oracle as so
+
+    T = tk.classical_clock(tk.ZNIrrep[4], 4, 0.88) if model == "clock4_z4" else MODELS[model][0](tk)
+    ref = np.array(o.run(so.TRG_sym(np.asarray(T), T.charges, T.signs, T.N), chi, 10))
+    got = np.array(tk.run(tk.TRG(T), tk.truncrank(chi), tk.maxiter(10), verbosity=0))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL

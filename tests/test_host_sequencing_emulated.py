@@ -118,6 +118,22 @@ def test_emulated_models_testset_block_sparse(tk, emu, model):
     assert abs((f - answer) / answer) < tol
 
 
+@pytest.mark.parametrize("chi", [16, 13])
+@pytest.mark.parametrize("model", ["xy_u1", "sixvertex_u1", "phi4_complex_u1", "clock4_z4"])
+def test_block_sparse_trg_equals_sector_oracle_with_degenerate_sectors(tk, emu, model, chi):
+    """TensorKit semantics (oracle/sym_oracle.py: per-sector SVD, chi largest values over all
+    sectors) on tensors whose +-q (U(1)) or clock sectors are EXACTLY degenerate, with cuts through
+    the multiplets (chi = 13): the dense charge-basis oracle is not a valid reference there (its
+    SVD mixes the degenerate sectors), the sector oracle is, and the block-sparse TRG agrees with
+    it to rounding over 10 RG steps."""
+    import sym_oracle as so
+
+    T = tk.classical_clock(tk.ZNIrrep[4], 4, 0.88) if model == "clock4_z4" else _model(tk, model)[0]
+    ref = np.array(o.run(so.TRG_sym(np.asarray(T), T.charges, T.signs, T.N), chi, 10))
+    got = np.array(tk.run(tk.TRG(T), tk.truncrank(chi), tk.maxiter(10), verbosity=0))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-12
+
+
 def test_u1_tensor_bookkeeping(tk, emu):
     """SymTensor with N = 0: conservation without a modulus, coupled sectors keyed by the sum."""
     legs = [tk.Leg({-1: 2, 0: 1, 2: 3}, +1), tk.Leg({-2: 1, 1: 2}, +1), tk.Leg({-1: 2, 0: 2, 3: 1}, -1)]
