@@ -2,10 +2,11 @@
 (`src/models stays unchanged; model tensors are built on the host and uploaded once`).
 
 Each constructor returns a host `numpy` array indexed [leg1, leg2, ...] in the reference's
-leg convention (2D: V1 (x) V2 <- V3 (x) V4, 3D: D U' <- N E S' W').  `Z2Irrep` / `ZNIrrep`
-variants return the tensor in the charge basis (every leg graded by the irrep label); the
-engine currently stores them densely, which reproduces the symmetric result whenever the
-truncation does not cut through an exactly degenerate multiplet."""
+leg convention (2D: V1 (x) V2 <- V3 (x) V4, 3D: D U' <- N E S' W').  `Z2Irrep` / `ZNIrrep` /
+`U1Irrep` variants return a `ChargedArray`: the tensor in the charge basis (every leg graded by
+the irrep label) together with the charges and arrows of its legs, from which the schemes build
+the block-sparse device tensor (`symmetric.SymTensor`).  Non-abelian sectors (`DNIrrep`,
+`CU1Irrep`), product sectors and the fermionic models are not built."""
 from __future__ import annotations
 
 import math
