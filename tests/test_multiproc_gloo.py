@@ -106,3 +106,51 @@ def test_block_sparse_hotrg3d_sharded_world2(chi, n):
         assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, r
         assert plan["world"] == 2 and plan["chunks"] >= 2 and plan["my_F_chunks"] >= 1
     assert res[0][0] == res[1][0]           # replicas stay bit-identical
+
+
+def _sym_atrg_worker(rank, world, port, chi, n, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tnrkit.jl_b200 as tk
+    from abi_emulator import EmulatedContext
+    from tnrkit.jl_b200 import _lib, symmetric
+
+    _lib._default_ctx = EmulatedContext()   # numpy emulation of the C-ABI primitives (tests only)
+    s = tk.ATRG_3D(tk.classical_ising_3D(), symmetric=True, shard=True)
+    assert s.sym and s.shard
+    got = tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
+    q.put((rank, got, dict(symmetric.LAST_PLAN["atrg3d"])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chi,n", [(4, 3), (6, 2)])
+def test_block_sparse_atrg3d_sharded_world2(chi, n):
+    """Block-sparse (Z2) ATRG_3D with the chunks of the open bond of AX / YD dealt to two ranks:
+    TSQR stacks of the chunk R factors and H / G each replicated by one all-reduce of a flat
+    block buffer.  Norm list == oracle on both ranks, replicas bit-identical."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tnr_oracle as o
+
+    import tnrkit.jl_b200 as tk
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sym_atrg_worker, args=(r, 2, port, chi, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (got, plan) for r, got, plan in (q.get(timeout=300) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = np.array(o.run(o.ATRG_3D(np.asarray(tk.classical_ising_3D())), chi, n))
+    for r in range(2):
+        got, plan = res[r]
+        assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, r
+        assert plan["world"] == 2 and plan["chunks_AX"] >= 2 and plan["my_chunks"] >= 2
+    assert res[0][0] == res[1][0]           # replicas stay bit-identical

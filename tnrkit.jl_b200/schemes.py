@@ -224,7 +224,7 @@ class ATRG_3D(_Sym3D, TNRScheme):
     DENSE_BYTES_LIMIT = 150e9
 
     def __init__(self, T, ctx=None, symmetric=None, factored=None, shard=None, group=None,
-                 max_chunk_elems=1 << 30, tol=1e-13, block=None, rfactor="tsqr"):
+                 max_chunk_elems=1 << 30, tol=1e-13, block=None, rfactor="tsqr", sym_chunk=None):
         self._F = None
         self.block = block
         self.rfactor = rfactor
@@ -233,9 +233,13 @@ class ATRG_3D(_Sym3D, TNRScheme):
         self.max_chunk_elems = int(max_chunk_elems)
         self.tol = float(tol)
         if self._init_sym3d(T, symmetric, ctx):
-            if factored or shard:
-                raise NotImplementedError("factored / sharded ATRG_3D on block-sparse tensors")
-            self.factored = self.shard = False
+            if factored:
+                raise NotImplementedError("factored ATRG_3D on block-sparse tensors")
+            # block-sparse: shard=True deals the chunks of the open bond of AX / YD to the ranks
+            # (symmetric.py: _atrg3d_tail_sharded); `sym_chunk` chunks it on one process as well
+            self.factored = False
+            self.shard = bool(shard)
+            self.sym_chunk = sym_chunk
             return
         TNRScheme.__init__(self, T, ctx)
         if shard and factored is False:
@@ -282,7 +286,12 @@ class ATRG_3D(_Sym3D, TNRScheme):
         if self.sym:
             from .symmetric import atrg3d_step_sym
 
-            self.T = atrg3d_step_sym(self.T, chi)
+            shard = None
+            if self.shard:
+                import torch.distributed as dist
+
+                shard = (dist.get_rank(self.group), dist.get_world_size(self.group), self.group)
+            self.T = atrg3d_step_sym(self.T, chi, shard, self.sym_chunk)
             return self
         if self.factored is None:
             self.factored = self.wants_factored(chi)

@@ -728,10 +728,117 @@ def _atrg3d_projectors_sym(Rl: SymTensor, Rr: SymTensor, chi: int):
     return Pa, Pb
 
 
-def atrg3d_substep_sym(T: SymTensor, chi: int) -> SymTensor:
+def _split_for(leg: Leg, world: int, size=None):
+    """Chunks of `leg` for `world` ranks: the widest chunk width (<= `size`) that still yields at
+    least `world` chunks (fewer only when the leg has fewer than `world` states)."""
+    c = max(leg.dims.values())
+    if size is not None:
+        c = max(1, min(c, int(size)))
+    while c > 1 and len(leg_chunks(leg, c)) < world:
+        c -= 1
+    return leg_chunks(leg, c)
+
+
+def _tsqr_orth_r(pieces, row_legs, col_legs, N, ctx, nslots, shard):
+    """R factor of a tall operand given as row chunks (TSQR): `pieces` = [(slot, R_slot)] are the
+    R factors [r(+); cols] of this rank's chunks; they are stacked along the bond -- slot s owns
+    rows [s n_c, (s+1) n_c) of coupled sector c (n_c = columns of that sector; unused rows stay
+    zero and drop out of R^T R) -- in ONE flat zero-initialised buffer, one all-reduce (sum of
+    disjoint supports: exact) replicates the stack, and its own R factor is the result.  Same
+    orthogonal gauge freedom as `_orth_r`.  Only coupled sectors that the full operand has
+    (`row_legs` x `col_legs`) enter, as in `SymTensor.matricize`."""
+    rank, world, group = shard
+    probe = SymTensor(N, list(row_legs) + list(col_legs), {}, ctx)
+    nrow = len(row_legs)
+    rt = probe._tuples(range(nrow), False)
+    ct = probe._tuples(range(nrow, nrow + len(col_legs)), True)
+    ncols = {c: v[-1][1] + v[-1][2] for c, v in ct.items() if c in rt}
+    stack_leg = Leg({c: nslots * n for c, n in ncols.items()}, +1)
+    stack, whole = sym_zeros(N, [stack_leg] + list(col_legs), ctx, flat=True)
+    for slot, R in pieces:
+        for key, blk in R.blocks.items():
+            dst_blk = stack.blocks[key]
+            bd = R.block_dims(key)
+            assert bd[0] <= ncols[key[0]]
+            dst = C.c_void_p(dst_blk.buf.data_ptr() + 8 * slot * ncols[key[0]])
+            ctx.call("tnr_strided_copy", blk.ptr, dst, len(bd), _lib.i64(bd),
+                     _lib.i64(_colmajor_strides(bd)),
+                     _lib.i64(_colmajor_strides(stack.block_dims(key))))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(whole, op=dist.ReduceOp.SUM, group=group)
+    return _orth_r(stack, 1)
+
+
+def _atrg3d_tail_sharded(gU, fU, fV, gV, chi: int, shard, chunk=None) -> SymTensor:
+    """atrg3d.jl:47-82 with the open bond -1 of AX and YD cut into chunks that are dealt
+    round-robin to the ranks `shard = (rank, world, group)`.  No rank forms a whole chi^6 tensor:
+    a chunk of AX / YD is contracted, reduced to its two R factors (rows of the tall
+    matricizations: TSQR, `_tsqr_orth_r`), and -- once the replicated projectors exist --
+    projected into its index range of H / G.  Exchanged: four R stacks (chi^2 x chi^2 per chunk)
+    and H, G (chi^4), each by one all-reduce of a flat block buffer with disjoint supports.
+    The two truncated SVDs in front of it (atrg3d.jl:35-45) stay replicated."""
+    rank, world, group = shard
+    N, ctx = gU.N, gU.ctx
+    q = (0, 1, 4, 5, 2, 3)
+
+    def passes(left, right, chunks):
+        # operand[-1 -2;-3 -4 -5 -6] := left[1 -2;-3 -5] right[-1 1;-4 -6], chunked along -1
+        mine = [(s, ch) for s, ch in enumerate(chunks) if s % world == rank]
+        legs = [left.legs[3], right.legs[0], right.legs[1], left.legs[1], right.legs[2], left.legs[2]]
+        parts, Ra, Rb = [], [], []
+        for s, ch in mine:
+            Z = sym_contract(sym_slice(left, 3, ch), "idfa", right, "bcei", "abcdef")
+            Ra.append((s, _orth_r(Z, 4)))                    # [r; 5 6]
+            Rb.append((s, _orth_r(Z.permute(q), 4)))         # [r; 3 4]
+            parts.append((ch, Z))
+        n = len(chunks)
+        R56 = _tsqr_orth_r(Ra, legs[:4], legs[4:], N, ctx, n, shard)
+        R34 = _tsqr_orth_r(Rb, legs[:2] + legs[4:], legs[2:4], N, ctx, n, shard)
+        return parts, legs, R56, R34
+
+    cA = _split_for(gU.legs[3], world, chunk)
+    cY = _split_for(fV.legs[3], world, chunk)
+    LAST_PLAN["atrg3d"] = {"world": world, "chunks_AX": len(cA), "chunks_YD": len(cY),
+                           "my_chunks": sum(1 for s in range(len(cA)) if s % world == rank)
+                           + sum(1 for s in range(len(cY)) if s % world == rank)}
+    # AX[-1 -2;-3 -4 -5 -6] := A[1 -2;-3 -5] X[-1 1;-4 -6];  YD := Y[1 -2;-3 -5] D[-1 1;-4 -6]
+    ax_parts, ax_legs, R2t, R4t = passes(gU, fU, cA)
+    yd_parts, yd_legs, R1, R3 = passes(fV, gV, cY)
+    P1, P2 = _atrg3d_projectors_sym(R1, R2t.permute((1, 2, 0)), chi)
+    P3, P4 = _atrg3d_projectors_sym(R3, R4t.permute((1, 2, 0)), chi)
+
+    def project(parts, legs, Pc, lc, Pd, ld):
+        out, whole = sym_zeros(N, [legs[0], legs[1], Pc.legs[lc.index("c")], Pd.legs[ld.index("d")]],
+                               ctx, flat=True)
+        for ch, Z in parts:
+            piece = sym_contract(sym_contract(Z, "abijkl", Pc, lc, "abklc"), "abklc", Pd, ld, "abcd")
+            sym_scatter(out, piece, {0: ch})
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(whole, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    # H[-1 -2;-3 -4] := YD[-1 -2;1 2 3 4] Proj_3[1 2;-3] Proj_1[3 4;-4]
+    H = project(yd_parts, yd_legs, P3, "ijc", P1, "kld")
+    del yd_parts
+    # G[-1 -2;-3 -4] := AX[-1 -2;1 2 3 4] Proj_4[-3;1 2] Proj_2[-4;3 4]
+    G = project(ax_parts, ax_legs, P4, "cij", P2, "dkl")
+    del ax_parts
+    # T[-1 -2;-3 -4 -5 -6] := G[1 -2;-5 -6] H[-1 1;-3 -4]
+    return sym_contract(H, "aicd", G, "ibef", "abcdef")
+
+
+def atrg3d_substep_sym(T: SymTensor, chi: int, shard=None, chunk=None) -> SymTensor:
     """_step!(::ATRG_3D) on a Z_N tensor -- src/schemes/atrg3d.jl:34-83.  `permute(X, ((4,1),(2,3)))`
     of the reference is expressed through leg labels instead of data movement, as in the dense
-    engine (csrc/schemes.cu: atrg3d_substep)."""
+    engine (csrc/schemes.cu: atrg3d_substep).
+
+    `shard = (rank, world, group)` (or `chunk` = a chunk width on one process): AX / YD are
+    never formed whole, their open bond -1 is chunked and the chunks are dealt to the ranks
+    (`_atrg3d_tail_sharded`)."""
     perm = (1, 4, 5, 2, 3, 0)   # ((2,5,6),(3,4,1))
     fU, fS, fV, _ = sym_svd_trunc(T.permute(perm), 3, chi)     # U [i2 i5 i6 k], V [k i3 i4 i1]
     US = sym_clone(fU).scale_leg(3, fS)
@@ -744,6 +851,9 @@ def atrg3d_substep_sym(T: SymTensor, chi: int) -> SymTensor:
     rs = vec_map(gS, 1)
     gU.scale_leg(3, rs)    # X
     gV.scale_leg(0, rs)    # Y
+    if (shard is not None and shard[1] > 1) or chunk is not None:
+        return _atrg3d_tail_sharded(gU, fU, fV, gV, chi, shard if shard is not None
+                                    else (0, 1, None), chunk)
     # AX[-1 -2;-3 -4 -5 -6] := A[1 -2;-3 -5] X[-1 1;-4 -6];  YD := Y[1 -2;-3 -5] D[-1 1;-4 -6]
     AX = sym_contract(gU, "idfa", fU, "bcei", "abcdef")
     YD = sym_contract(fV, "idfa", gV, "bcei", "abcdef")
@@ -762,8 +872,8 @@ def atrg3d_substep_sym(T: SymTensor, chi: int) -> SymTensor:
     return sym_contract(H, "aicd", G, "ibef", "abcdef")
 
 
-def atrg3d_step_sym(T: SymTensor, chi: int) -> SymTensor:
+def atrg3d_step_sym(T: SymTensor, chi: int, shard=None, chunk=None) -> SymTensor:
     """step!(::ATRG_3D) on a Z_N tensor -- src/schemes/atrg3d.jl:85-97."""
     for _ in range(3):
-        T = atrg3d_substep_sym(T, chi).permute((3, 5, 1, 4, 0, 2))   # ((4,6),(2,5,1,3))
+        T = atrg3d_substep_sym(T, chi, shard, chunk).permute((3, 5, 1, 4, 0, 2))   # ((4,6),(2,5,1,3))
     return T
