@@ -141,6 +141,10 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             TNR_CHECK(value == 0 || (value >= 4 && value <= 10), "ozaki: 0 (off) or 4..10 digit planes");
             ctx->c.ozaki_slices = (int)value;
         }
+        else if (std::strcmp(key, "permute_unroll") == 0) {
+            TNR_CHECK(value == 1 || value == 2 || value == 4, "permute_unroll: 1 (default), 2 or 4");
+            ctx->c.permute_unroll = (int)value;
+        }
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;

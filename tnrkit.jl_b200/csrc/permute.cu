@@ -101,9 +101,95 @@ __global__ void __launch_bounds__(256) copy_tiled_kernel(const double* __restric
     }
 }
 
-// same fastest index on both sides: one thread per element, inner index fastest
-__global__ void __launch_bounds__(256) copy_rows_kernel(const double* __restrict__ src,
-                                                        double* __restrict__ dst,
+// copy_tiled_kernel with U rows of the read phase in flight per warp.  In the kernel above every
+// thread waits for its one outstanding 8-byte load before it can store it to shared memory
+// (768 threads x 8 B per SM in flight: the 48 % of the HBM roof measured in round 1); here a
+// thread issues up to 3 U independent loads (composite run <= 96 doubles = 3 per lane) before the
+// first store.  Same tiling, same parameters, same write phase.  Opt-in: tnr_set_option
+// "permute_unroll" = 2 | 4 (not yet measured on a B200).
+template <int U>
+__global__ void __launch_bounds__(256) copy_tiled_mlp_kernel(const double* __restrict__ src,
+                                                             double* __restrict__ dst,
+                                                             const CopyParams p) {
+    extern __shared__ double tile[];  // [TJ1*TJ2][pitch]
+    long long bid = blockIdx.x;
+    long long t_i1 = bid % p.tiles_i1; bid /= p.tiles_i1;
+    long long t_i2 = bid % p.tiles_i2; bid /= p.tiles_i2;
+    long long t_j1 = bid % p.tiles_j1; bid /= p.tiles_j1;
+    long long t_j2 = bid % p.tiles_j2; bid /= p.tiles_j2;
+    long long soff = 0, doff = 0;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+        if (d < p.rank) {
+            long long i = bid % p.dims[d];
+            bid /= p.dims[d];
+            soff += i * p.ss[d];
+            doff += i * p.ds[d];
+        }
+    }
+    const long long i10 = t_i1 * p.TI1, i20 = t_i2 * p.TI2, j10 = t_j1 * p.TJ1, j20 = t_j2 * p.TJ2;
+    const int ti1 = (int)min((long long)p.TI1, p.n_i1 - i10);
+    const int ti2 = (int)min((long long)p.TI2, p.n_i2 - i20);
+    const int tj1 = (int)min((long long)p.TJ1, p.n_j1 - j10);
+    const int tj2 = (int)min((long long)p.TJ2, p.n_j2 - j20);
+    const int ci = ti1 * ti2, cj = tj1 * tj2;   // composite extents of this tile (each <= 96)
+    const double* sp = src + soff + i10 * p.s_i1 + i20 * p.s_i2 + j10 * p.s_j1 + j20 * p.s_j2;
+    double* dp = dst + doff + i10 * p.d_i1 + i20 * p.d_i2 + j10 * p.d_j1 + j20 * p.d_j2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = p.pitch;
+    {
+        const long long lane_s = lane * p.s_i1, step_s = 32 * p.s_i1;
+        int j1 = warp % tj1, j2 = warp / tj1;
+        const int dj1 = 8 % tj1, dj2 = 8 / tj1;
+        for (int r0 = warp; r0 < cj; r0 += 8 * U) {
+            double v[U][3];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < cj) {
+                    const double* g = sp + j1 * p.s_j1 + j2 * p.s_j2 + lane_s;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (lane + 32 * k < ci) v[u][k] = g[k * step_s];
+                }
+                j1 += dj1; j2 += dj2;
+                if (j1 >= tj1) { j1 -= tj1; ++j2; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < cj) {
+                    double* t = tile + r * pitch + lane;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (lane + 32 * k < ci) t[32 * k] = v[u][k];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const long long lane_d = lane * p.d_j1, step_d = 32 * p.d_j1;
+        int i1 = warp % ti1, i2 = warp / ti1;
+        const int di1 = 8 % ti1, di2 = 8 / ti1;
+        for (int r = warp; r < ci; r += 8) {
+            double* g = dp + i1 * p.d_i1 + i2 * p.d_i2 + lane_d;
+            const double* t = tile + lane * pitch + r;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < cj) g[k * step_d] = t[32 * k * pitch];
+            i1 += di1; i2 += di2;
+            if (i1 >= ti1) { i1 -= ti1; ++i2; }
+        }
+    }
+}
+
+// same fastest index on both sides: one thread per element, inner index fastest.  T = double2
+// (opt-in with "permute_unroll" > 1): the inner run is contiguous and even on both sides and every
+// other stride is even, so the copy is the same strided copy on 16-byte elements.
+template <typename T>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const T* __restrict__ src,
+                                                        T* __restrict__ dst,
                                                         const CopyParams p) {
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= p.total) return;
@@ -218,7 +304,17 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
             p.rank++;
         }
         p.total = total;
-        copy_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, p);
+        bool vec = ctx->permute_unroll > 1 && p.si_s == 1 && p.si_d == 1 && p.ni % 2 == 0 &&
+                   (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
+        for (int d = 0; vec && d < p.rank; ++d) vec = p.ss[d] % 2 == 0 && p.ds[d] % 2 == 0;
+        if (vec) {
+            p.ni /= 2; p.total /= 2;
+            for (int d = 0; d < p.rank; ++d) { p.ss[d] /= 2; p.ds[d] /= 2; }
+            copy_rows_kernel<double2><<<(unsigned)((p.total + 255) / 256), 256, 0, ctx->stream>>>(
+                reinterpret_cast<const double2*>(src), reinterpret_cast<double2*>(dst), p);
+        } else {
+            copy_rows_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, p);
+        }
     } else {
         // i1 = source-fastest group, j1 = destination-fastest group (m[0]); i2 / j2 = the
         // groups that continue them contiguously in the source / destination, if any
@@ -265,9 +361,20 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         if (!configured) {
             TNR_CUDA(cudaFuncSetAttribute(copy_tiled_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            TNR_CUDA(cudaFuncSetAttribute(copy_tiled_mlp_kernel<2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            TNR_CUDA(cudaFuncSetAttribute(copy_tiled_mlp_kernel<4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             configured = true;
         }
-        copy_tiled_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
+        // the unrolled kernel holds a composite run in 3 registers per row: needs runs <= 96
+        const bool mlp = ctx->permute_unroll > 1 && p.TI1 * p.TI2 <= 96 && p.TJ1 * p.TJ2 <= 96;
+        if (mlp && ctx->permute_unroll >= 4)
+            copy_tiled_mlp_kernel<4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
+        else if (mlp)
+            copy_tiled_mlp_kernel<2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
+        else
+            copy_tiled_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(src, dst, p);
     }
     TNR_CUDA(cudaGetLastError());
     ctx->ctr.launches++;

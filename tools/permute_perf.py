@@ -1,4 +1,7 @@
-"""HBM throughput of the permute kernels on the shapes of a chi=24 HOTRG_3D step."""
+"""HBM throughput of the permute kernels on the shapes of a chi=24 HOTRG_3D step, for the default
+kernels (permute_unroll = 1) and the opt-in variants with more loads in flight (2, 4).
+
+    python tools/permute_perf.py [chi]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,17 +16,29 @@ cases = [("rotate ((6,4),(2,3,1,5))", (chi,) * 6, (5, 3, 1, 2, 0, 4)),
          ("Gram operand [K|z x]", (chi,) * 6, (1, 2, 3, 4, 0, 5)),
          ("matrix transpose", (chi ** 3, chi ** 3), (1, 0)),
          ("flat copy", (chi ** 6,), (0,))]
-for name, dims, perm in cases:
-    n = 1
-    for d in dims: n *= d
-    src = torch.randn(n, dtype=torch.float64, device="cuda")
-    dst = torch.empty_like(src)
-    def run():
-        ctx.call("tnr_permute", src.data_ptr(), dst.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
-    run(); torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record(); e1.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
+for unroll in (1, 2, 4):
+    ctx.set_option("permute_unroll", unroll)
+    print(f"--- permute_unroll = {unroll}", flush=True)
+    for name, dims, perm in cases:
+        n = 1
+        for d in dims: n *= d
+        src = torch.randn(n, dtype=torch.float64, device="cuda")
+        dst = torch.empty_like(src)
+        def run():
+            ctx.call("tnr_permute", src.data_ptr(), dst.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
+        run(); torch.cuda.synchronize()
+        if unroll > 1:   # same bits as the default kernels
+            ctx.set_option("permute_unroll", 1)
+            ref = torch.empty_like(src)
+            ctx.call("tnr_permute", src.data_ptr(), ref.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
+            ctx.set_option("permute_unroll", unroll)
+            torch.cuda.synchronize()
+            assert torch.equal(ref, dst), name
+            del ref
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
+ctx.set_option("permute_unroll", 1)
