@@ -74,3 +74,22 @@ def test_block_sparse_trg_equals_sector_oracle_on_device(tk, model, chi):
     ref = np.array(o.run(so.TRG_sym(np.asarray(T), T.charges, T.signs, T.N), chi, 10))
     got = np.array(tk.run(tk.TRG(T), tk.truncrank(chi), tk.maxiter(10), verbosity=0))
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+
+
+@pytest.mark.parametrize("name", ["TRG", "BTRG", "HOTRG", "ATRG"])
+@pytest.mark.parametrize("model", ["ising_trivial", "ising_z2", "sixvertex_u1"])
+def test_spaces_testset(tk, name, model):
+    """test/spaces.jl:5-24: every 2D scheme takes every kind of space through 25 steps at the odd
+    truncrank(7) without a space mismatch (Gross-Neveu is fermionic: out of scope).  CPU twin:
+    tests/test_host_sequencing_emulated.py::test_emulated_spaces_testset."""
+    T = {"ising_trivial": lambda: tk.classical_ising(tk.Trivial),
+         "ising_z2": lambda: tk.classical_ising(),
+         "sixvertex_u1": lambda: tk.sixvertex(tk.U1Irrep)}[model]()
+    s = getattr(tk, name)(T)
+    assert s.sym == (model != "ising_trivial")
+    data = tk.run(s, tk.truncrank(7), tk.maxiter(25), verbosity=0)
+    assert len(data) == 26 and all(np.isfinite(x) and x > 0 for x in data)
+    assert max(s.T.dims) <= 7
+    if s.sym:
+        for key in s.T.blocks:
+            assert s.T.allowed(key)

@@ -237,3 +237,25 @@ def test_emulated_atrg3d_chunked_tail_matches_oracle(tk, emu, chi, n, chunk):
     base = np.array(tk.run(tk.ATRG_3D(T, symmetric=True), tk.truncrank(chi), tk.maxiter(n),
                            verbosity=0))
     assert np.max(np.abs(got - base) / np.abs(base)) <= 1e-11
+
+
+@pytest.mark.parametrize("name", ["TRG", "BTRG", "HOTRG", "ATRG"])
+@pytest.mark.parametrize("model", ["ising_z2", "sixvertex_u1"])
+def test_emulated_spaces_testset(tk, emu, name, model):
+    """test/spaces.jl:5-24: every 2D scheme takes every kind of space through 25 steps at the odd
+    truncrank(7) without a space mismatch (here: the Z2 Ising and the U(1) six-vertex tensor on
+    the block-sparse path; `classical_ising(Trivial)` runs on the dense device path, GPU twin in
+    tests/test_gpu_zz_models_u1.py; the Gross-Neveu tensor is fermionic: out of scope).  On top
+    of the reference's `isa(..., Any)`: all 26 norms are finite and positive, every block obeys
+    the conservation law, and contracted bonds keep opposite arrows."""
+    T = tk.classical_ising() if model == "ising_z2" else tk.sixvertex(tk.U1Irrep)
+    s = getattr(tk, name)(T)
+    assert s.sym
+    data = tk.run(s, tk.truncrank(7), tk.maxiter(25), verbosity=0)
+    assert len(data) == 26 and all(np.isfinite(x) and x > 0 for x in data)
+    assert max(s.T.dims) <= 7
+    for key in s.T.blocks:
+        assert s.T.allowed(key)
+    # horizontal / vertical bonds of the final tensor can still be contracted with themselves
+    assert s.T.legs[0].sign == -s.T.legs[3].sign and s.T.legs[0].same_space(s.T.legs[3])
+    assert s.T.legs[1].sign == -s.T.legs[2].sign and s.T.legs[1].same_space(s.T.legs[2])
