@@ -489,3 +489,93 @@ def finalize_two_by_two(scheme):
     f = n ** 0.25
     scheme.T = T / f
     return f
+
+
+# ---- observables of the fixed-point tensor (src/utility/cft.jl) and their finalizers ----------
+ising_cft_exact = [1 / 8, 1, 9 / 8, 9 / 8, 2, 2, 2, 2, 17 / 8, 17 / 8, 17 / 8, 3, 3, 3, 3, 3]
+
+
+def _unit_tensor(scheme):
+    """BTRG: T_unit[-1 -2;-3 -4] := T[1 2;-3 -4] S1[-2;2] S2[-1;1] (cft.jl:44-45, 319-320,
+    386-387); every other scheme: T itself."""
+    if isinstance(scheme, BTRG):
+        return np.einsum("abcd,yb,xa->xycd", scheme.T, scheme.S1, scheme.S2, optimize=_OPT)
+    return scheme.T
+
+
+def transfer_matrix(scheme, unitcell=1):
+    """ncon(fill(T, u), [[i, -i, -(i+u), i+1] ...; last leg 4 -> 1]) permuted to
+    ((1..u), (u+1..2u)) -- cft.jl:7-16 / 280-295: a ring of u tensors along legs 1/4, matrix
+    from the legs 2 (rows) to the legs 3 (columns)."""
+    T = _unit_tensor(scheme)
+    R = T                                   # [a, b1.., c1.., d]
+    for i in range(1, unitcell):
+        # contract the running leg d with leg 1 of the next tensor
+        R = np.tensordot(R, T, axes=([R.ndim - 1], [0]))      # [a, b.., c.., b', c', d']
+        nb = i
+        order = [0] + list(range(1, 1 + nb)) + [1 + 2 * nb] + list(range(1 + nb, 1 + 2 * nb)) + \
+            [2 + 2 * nb, 3 + 2 * nb]
+        R = np.transpose(R, order)          # [a, b.., b', c.., c', d']
+    R = np.trace(R, axis1=0, axis2=R.ndim - 1)
+    n = int(np.prod(R.shape[:unitcell]))
+    return R.reshape(n, -1)
+
+
+def cft_data(scheme, v=1, unitcell=1, is_real=True):
+    """cft.jl:5-37 (TNRScheme) and 39-73 (BTRG): scaling dimensions from the eigenvalues of the
+    transfer matrix."""
+    data = np.linalg.eigvals(transfer_matrix(scheme, unitcell)).astype(complex)
+    data = data[np.argsort(-np.abs(data), kind="stable")]
+    data = data[data.real > 0]
+    data = data[np.abs(data) > 1.0e-12]
+    if is_real:
+        data = data.real
+    return unitcell * (1 / (2 * math.pi * v)) * np.log(data[0] / data)
+
+
+def central_charge(scheme, n):
+    """cft.jl:256-260: M[-1;-2] := (T / n)[1 -1;-2 1], c = 6/pi log(sigma_max(M));
+    BTRG (cft.jl:262-269): M := T[1 -1;3 2] S1[3;-2] S2[2;1] / n."""
+    if isinstance(scheme, BTRG):
+        M = np.einsum("abcd,cy,da->by", scheme.T, scheme.S1, scheme.S2, optimize=_OPT) / n
+    else:
+        M = np.einsum("abca->bc", scheme.T) / n
+    return math.log(np.linalg.svd(M, compute_uv=False)[0]) * 6 / math.pi
+
+
+def ground_state_degeneracy(scheme, unitcell=1):
+    """cft.jl:278-309 / 311-339: exp of the Shannon entropy of the normalised transfer-matrix
+    spectrum."""
+    D = np.linalg.eigvals(transfer_matrix(scheme, unitcell))
+    D = D / np.sum(D)
+    vals = np.abs(D)
+    vals = vals[vals > 0]
+    return float(np.exp(-np.sum(vals * np.log(vals))))
+
+
+def gu_wen_ratio(scheme):
+    """cft.jl:374-383 / 385-395: X1 = |T[1 2;2 1]|^2 / |T[1 2;2 3] T[3 4;4 1]|,
+    X2 = |T[1 2;2 1]|^2 / |T[1 2;3 4] T[4 3;2 1]|."""
+    T = _unit_tensor(scheme)
+    one = abs(np.einsum("abba->", T))
+    x1 = abs(np.einsum("abbc,cdda->", T, T))
+    x2 = abs(np.einsum("abcd,dcba->", T, T))
+    return one ** 2 / x1, one ** 2 / x2
+
+
+def finalize_central_charge(scheme):
+    """finalize.jl:143-146."""
+    n = scheme.finalize()
+    return central_charge(scheme, n)
+
+
+def finalize_groundstatedegeneracy(scheme):
+    """finalize.jl:153-161."""
+    scheme.finalize()
+    return ground_state_degeneracy(scheme, 1)
+
+
+def finalize_gu_wen_ratio(scheme):
+    """finalize.jl:171-179."""
+    scheme.finalize()
+    return gu_wen_ratio(scheme)

@@ -259,3 +259,67 @@ def test_emulated_spaces_testset(tk, emu, name, model):
     # horizontal / vertical bonds of the final tensor can still be contracted with themselves
     assert s.T.legs[0].sign == -s.T.legs[3].sign and s.T.legs[0].same_space(s.T.legs[3])
     assert s.T.legs[1].sign == -s.T.legs[2].sign and s.T.legs[1].same_space(s.T.legs[2])
+
+
+def _oracle_twin(tk, name, s):
+    """Oracle scheme object holding the same state as the product scheme `s`."""
+    dense = s.T.to_dense() if s.sym else s.T.to_numpy()
+    os_ = getattr(o, name)(dense)
+    if name == "BTRG":
+        if s.sym:
+            w = lambda S, leg: np.concatenate([S[q].to_numpy().reshape(-1) for q in s.T.legs[leg].charges])
+            os_.S1, os_.S2 = np.diag(w(s.S1, 1)), np.diag(w(s.S2, 0))
+        else:
+            os_.S1, os_.S2 = np.diag(s.S1.to_numpy().reshape(-1)), np.diag(s.S2.to_numpy().reshape(-1))
+    return os_
+
+
+@pytest.mark.parametrize("name", ["TRG", "BTRG", "HOTRG", "ATRG"])
+def test_emulated_cft_observables_match_oracle(tk, emu, name):
+    """cft_data / central_charge / ground_state_degeneracy / gu_wen_ratio (tnrkit.jl_b200/cft.py;
+    reference: src/utility/cft.jl) and their finalizers on a block-sparse scheme after a few RG
+    steps: same numbers as the oracle's restatement on the same state (unit cells 1 and 2)."""
+    s = getattr(tk, name)(tk.classical_ising(o.ising_bc + 0.01))
+    assert s.sym
+    tk.run(s, tk.truncrank(8), tk.maxiter(6), verbosity=0)
+    tw = _oracle_twin(tk, name, s)
+    for u in (1, 2):
+        got, ref = tk.cft_data(s, unitcell=u), o.cft_data(tw, unitcell=u)
+        k = min(6, len(ref))
+        assert len(got) == len(ref) and np.abs(got[:k] - ref[:k]).max() <= 1e-9
+        assert abs(tk.ground_state_degeneracy(s, u) - o.ground_state_degeneracy(tw, u)) <= 1e-10
+    assert np.abs(np.array(tk.gu_wen_ratio(s)) - np.array(o.gu_wen_ratio(tw))).max() <= 1e-10
+    assert abs(tk.central_charge(s, 1.7) - o.central_charge(tw, 1.7)) <= 1e-10
+    # finalizer forms through run!: one entry per step plus the initial one
+    s2 = getattr(tk, name)(tk.classical_ising(o.ising_bc + 0.01))
+    data = tk.run(s2, tk.truncrank(8), tk.maxiter(3), tk.guwenratio_Finalizer, verbosity=0)
+    assert len(data) == 4 and all(len(d) == 2 for d in data)
+    tw2 = getattr(o, name)(o.classical_ising(o.ising_bc + 0.01))
+    ref = [o.finalize_gu_wen_ratio(tw2)]
+    for _ in range(3):
+        tw2.step(8)
+        ref.append(o.finalize_gu_wen_ratio(tw2))
+    assert np.abs(np.array(data) - np.array(ref)).max() <= 1e-9
+    assert abs(tk.finalize_groundstatedegeneracy(s2) - o.finalize_groundstatedegeneracy(tw2)) <= 1e-9
+    assert abs(tk.finalize_central_charge(s2) - o.finalize_central_charge(tw2)) <= 1e-9
+
+
+def test_emulated_cft_observables_dense_tensor(tk, emu):
+    """The dense (`Trivial`) form of the same functions: the state of an oracle BTRG / TRG run is
+    loaded into dense product schemes."""
+    for name in ("TRG", "BTRG"):
+        tw = getattr(o, name)(o.classical_ising(o.ising_bc - 0.01))
+        o.run(tw, 8, 5)
+        s = getattr(tk, name)(tk.classical_ising(tk.Trivial))
+        assert not s.sym
+        s.T = tk.DeviceTensor.from_numpy(tw.T, 2, emu)
+        if name == "BTRG":
+            s.S1 = tk.DeviceTensor.from_numpy(np.diag(tw.S1).copy(), 1, emu)
+            s.S2 = tk.DeviceTensor.from_numpy(np.diag(tw.S2).copy(), 1, emu)
+        assert np.abs(tk.cft_data(s)[:5] - o.cft_data(tw)[:5]).max() <= 1e-10
+        assert np.abs(tk.cft_data(s, unitcell=3)[:5] - o.cft_data(tw, unitcell=3)[:5]).max() <= 1e-9
+        assert abs(tk.ground_state_degeneracy(s) - o.ground_state_degeneracy(tw)) <= 1e-10
+        assert np.abs(np.array(tk.gu_wen_ratio(s)) - np.array(o.gu_wen_ratio(tw))).max() <= 1e-10
+        assert abs(tk.central_charge(s, 0.9) - o.central_charge(tw, 0.9)) <= 1e-10
+    with pytest.raises(TypeError):
+        tk.cft_data(tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=False))

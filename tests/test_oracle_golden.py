@@ -140,3 +140,31 @@ def test_ozaki_model_digit_planes_are_error_free():
     e7 = float(np.max(np.abs(om.multiply(A, B, 7) - ref) / scale_ab))
     ed = float(np.max(np.abs(A @ B.T - ref) / scale_ab))
     assert e8 <= 2e-15 and ed <= 2e-15 and e7 <= 3e-13 and e8 < e7
+
+
+# ---- observables of the coarse-grained tensor (src/utility/cft.jl), pinned to test/schemes.jl ----
+@pytest.mark.parametrize("name,chi,n,r1,r2", [("TRG", 24, 10, 2.0e-4, 1.0e-2), ("BTRG", 24, 10, 3.0e-4, 2.0e-2),
+                                              ("HOTRG", 16, 4, 6.0e-4, 1.0e-2), ("ATRG", 24, 3, 1.0e-2, 1.0e-2)])
+def test_oracle_cft_data_reference_testsets(name, chi, n, r1, r2):
+    """`cft_data(scheme)[2:end]` against `ising_cft_exact` at the reference's own sizes and
+    tolerances -- test/schemes.jl:25-31 (TRG), 63-69 (BTRG), 100-106 (HOTRG), 137-143 (ATRG)."""
+    s = getattr(o, name)(o.classical_ising())
+    o.run(s, chi, n)
+    cft = o.cft_data(s)[1:]
+    assert abs(cft[0] - o.ising_cft_exact[0]) <= r1 * o.ising_cft_exact[0]
+    assert abs(cft[1] - o.ising_cft_exact[1]) <= r2 * o.ising_cft_exact[1]
+
+
+@pytest.mark.parametrize("name,chi", [("TRG", 16), ("BTRG", 16), ("HOTRG", 12), ("ATRG", 16)])
+@pytest.mark.parametrize("dbeta,want", [(-0.01, 1.0), (+0.01, 2.0)])
+def test_oracle_gsd_and_gu_wen_reference_testsets(name, chi, dbeta, want):
+    """`ground_state_degeneracy` and `gu_wen_ratio` on both sides of beta_c, rtol 1e-2 --
+    test/schemes.jl:33-54, 71-90, 108-127, 145-164."""
+    s = getattr(o, name)(o.classical_ising(o.ising_bc + dbeta))
+    o.run(s, chi, 20)
+    x1, x2 = o.gu_wen_ratio(s)
+    for got in (o.ground_state_degeneracy(s), x1, x2):
+        assert abs(got - want) <= 1.0e-2 * want
+    # the finalizer forms (finalize.jl:143-179) leave T normalised and return the same numbers
+    assert abs(o.finalize_groundstatedegeneracy(s) - want) <= 1.0e-2 * want
+    assert abs(o.finalize_gu_wen_ratio(s)[0] - want) <= 1.0e-2 * want

@@ -6,6 +6,9 @@ interface for that path: scheme constructors, `run!`, `truncrank`, `maxiter`,
 (hand-written CUDA for sm_100a) through the C ABI declared in include/tnrcuda.h."""
 from . import _lib
 from ._lib import Context, TNRCudaError, default_context
+from .cft import (GSDegeneracy_Finalizer, central_charge, central_charge_Finalizer, cft_data,
+                  finalize_central_charge, finalize_groundstatedegeneracy, finalize_gu_wen_ratio,
+                  ground_state_degeneracy, gu_wen_ratio, guwenratio_Finalizer, transfer_matrix)
 from .free_energy import free_energy
 from .models import (XY_bc, XY_βc, ChargedArray, Trivial, U1Irrep, Z2Irrep, ZNIrrep, classical_XY,
                      classical_clock,
