@@ -1,5 +1,5 @@
 """Opt-in permute kernels with several loads in flight per thread (`tnr_set_option
-"permute_unroll"` = 2 | 4: copy_tiled_mlp_kernel<U>, copy_rows_kernel<double2>, csrc/permute.cu)
+"permute_unroll"` = 2 | 4, `"permute_tile"` = 32 | 48 | 64: copy_tiled_mlp_kernel<U>, copy_rows_kernel<double2>, csrc/permute.cu)
 against numpy and against the default kernels -- pure data movement, bit exact.  Covers ragged
 tiles (extents that are no multiple of the 96-element composite run), odd extents (no 16-byte
 path), the equal-fastest-leg case and the chi = 24 rotation of hotrg3d.jl:134.
@@ -21,17 +21,19 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("unroll", [2, 4])
+@pytest.mark.parametrize("unroll,tile", [(2, 96), (4, 96), (4, 64), (1, 48), (4, 32)])
 @pytest.mark.parametrize("dims,perm", CASES)
-def test_permute_unrolled_kernels_bit_exact(tk, ctx, dims, perm, unroll):
+def test_permute_unrolled_kernels_bit_exact(tk, ctx, dims, perm, unroll, tile):
     rng = np.random.default_rng(len(dims) * 100 + unroll)
     a = rng.standard_normal(dims)
     T = tk.DeviceTensor.from_numpy(a)
     ctx.set_option("permute_unroll", unroll)
+    ctx.set_option("permute_tile", tile)
     try:
         got = T.permute(perm).to_numpy()
     finally:
         ctx.set_option("permute_unroll", 1)
+        ctx.set_option("permute_tile", 96)
     assert np.array_equal(got, np.transpose(a, perm))
     assert np.array_equal(got, T.permute(perm).to_numpy())
 
@@ -39,7 +41,10 @@ def test_permute_unrolled_kernels_bit_exact(tk, ctx, dims, perm, unroll):
 def test_permute_unroll_option_is_validated(tk, ctx):
     with pytest.raises(tk.TNRCudaError):
         ctx.set_option("permute_unroll", 3)
+    with pytest.raises(tk.TNRCudaError):
+        ctx.set_option("permute_tile", 100)
     ctx.set_option("permute_unroll", 1)
+    ctx.set_option("permute_tile", 96)
 
 
 def test_hotrg3d_step_with_unrolled_permutes(tk, ctx):

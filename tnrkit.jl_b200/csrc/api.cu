@@ -141,6 +141,11 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             TNR_CHECK(value == 0 || (value >= 4 && value <= 10), "ozaki: 0 (off) or 4..10 digit planes");
             ctx->c.ozaki_slices = (int)value;
         }
+        else if (std::strcmp(key, "permute_tile") == 0) {
+            TNR_CHECK(value == 32 || value == 48 || value == 64 || value == 96,
+                      "permute_tile: 32, 48, 64 or 96 (default)");
+            ctx->c.permute_tile = (int)value;
+        }
         else if (std::strcmp(key, "permute_unroll") == 0) {
             TNR_CHECK(value == 1 || value == 2 || value == 4, "permute_unroll: 1 (default), 2 or 4");
             ctx->c.permute_unroll = (int)value;

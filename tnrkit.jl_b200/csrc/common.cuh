@@ -57,6 +57,7 @@ struct Context {
     bool disable_tma = false;  // force the cp.async GEMM (A/B testing)
     bool disable_subspace = false;  // force full Jacobi in eigh_trunc
     bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
+    int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
     int permute_unroll = 1;  // 2 | 4: permute kernels with several loads in flight per thread (opt-in)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems

@@ -324,7 +324,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
             if (i != js && m[i].s == m[js].s * m[js].n) i2 = i;
         for (size_t i = 1; i < m.size(); ++i)
             if (i != js && i != i2 && m[i].d == m[0].d * m[0].n) j2 = i;
-        const int TGT = 96;  // composite run length (doubles)
+        const int TGT = ctx->permute_tile;  // composite run length (doubles): 96, opt-in 32 | 48 | 64
         auto split = [&](long long n1, long long n2, int& T1, int& T2) {
             if (n1 >= TGT) { T1 = TGT; T2 = 1; }
             else if (n1 > 48 || n2 <= 1) { T1 = (int)std::min<long long>(n1, 48); T2 = 1;

@@ -16,9 +16,10 @@ cases = [("rotate ((6,4),(2,3,1,5))", (chi,) * 6, (5, 3, 1, 2, 0, 4)),
          ("Gram operand [K|z x]", (chi,) * 6, (1, 2, 3, 4, 0, 5)),
          ("matrix transpose", (chi ** 3, chi ** 3), (1, 0)),
          ("flat copy", (chi ** 6,), (0,))]
-for unroll in (1, 2, 4):
+for unroll, tile in [(1, 96), (2, 96), (4, 96), (4, 64), (4, 48), (1, 48), (4, 32)]:
     ctx.set_option("permute_unroll", unroll)
-    print(f"--- permute_unroll = {unroll}", flush=True)
+    ctx.set_option("permute_tile", tile)
+    print(f"--- permute_unroll = {unroll}, permute_tile = {tile}", flush=True)
     for name, dims, perm in cases:
         n = 1
         for d in dims: n *= d
@@ -27,11 +28,13 @@ for unroll in (1, 2, 4):
         def run():
             ctx.call("tnr_permute", src.data_ptr(), dst.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
         run(); torch.cuda.synchronize()
-        if unroll > 1:   # same bits as the default kernels
+        if (unroll, tile) != (1, 96):   # same bits as the default kernels
             ctx.set_option("permute_unroll", 1)
+            ctx.set_option("permute_tile", 96)
             ref = torch.empty_like(src)
             ctx.call("tnr_permute", src.data_ptr(), ref.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
             ctx.set_option("permute_unroll", unroll)
+            ctx.set_option("permute_tile", tile)
             torch.cuda.synchronize()
             assert torch.equal(ref, dst), name
             del ref
@@ -42,3 +45,4 @@ for unroll in (1, 2, 4):
             best = min(best, e0.elapsed_time(e1))
         print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
 ctx.set_option("permute_unroll", 1)
+ctx.set_option("permute_tile", 96)
