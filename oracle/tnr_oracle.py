@@ -492,7 +492,8 @@ def finalize_two_by_two(scheme):
 
 
 # ---- observables of the fixed-point tensor (src/utility/cft.jl) and their finalizers ----------
-ising_cft_exact = [1 / 8, 1, 9 / 8, 9 / 8, 2, 2, 2, 2, 17 / 8, 17 / 8, 17 / 8, 3, 3, 3, 3, 3]
+ising_cft_exact = [1 / 8, 1, 9 / 8, 9 / 8, 2, 2, 2, 2, 17 / 8, 17 / 8, 17 / 8, 3, 3, 3, 3, 3,
+                   25 / 8, 25 / 8, 25 / 8, 25 / 8, 25 / 8, 25 / 8]   # src/models/ising.jl:3-7
 
 
 def _unit_tensor(scheme):

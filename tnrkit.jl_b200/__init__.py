@@ -13,7 +13,7 @@ from .free_energy import free_energy
 from .models import (XY_bc, XY_βc, ChargedArray, Trivial, U1Irrep, Z2Irrep, ZNIrrep, classical_XY,
                      classical_clock,
                      classical_ising, classical_ising_3D, classical_potts, f_onsager, ising_bc,
-                     ising_bc_3D, ising_βc, ising_βc_3D, phi4_complex, phi4_real, potts_bc, potts_βc,
+                     ising_bc_3D, ising_cft_exact, ising_βc, ising_βc_3D, phi4_complex, phi4_real, potts_bc, potts_βc,
                      sixvertex)
 from .schemes import (ATRG, ATRG_3D, BTRG, HOTRG, HOTRG_3D, TRG, Finalizer, TNRScheme,
                       allgather_last_leg, beta_sweep, default_Finalizer, finalize,

@@ -65,6 +65,9 @@ class ZNIrrep:
 ising_βc = math.log(1.0 + math.sqrt(2.0)) / 2.0
 ising_bc = ising_βc
 f_onsager = -2.10965114460820745966777928351108478082549327543540531781696107967700291143188
+# src/models/ising.jl:3-7
+ising_cft_exact = [1 / 8, 1, 9 / 8, 9 / 8, 2, 2, 2, 2, 17 / 8, 17 / 8, 17 / 8, 3, 3, 3, 3, 3,
+                   25 / 8, 25 / 8, 25 / 8, 25 / 8, 25 / 8, 25 / 8]
 ising_βc_3D = 1.0 / 4.51152469
 ising_bc_3D = ising_βc_3D
 
