@@ -283,6 +283,11 @@ def test_emulated_cft_observables_match_oracle(tk, emu, name):
     assert s.sym
     tk.run(s, tk.truncrank(8), tk.maxiter(6), verbosity=0)
     tw = _oracle_twin(tk, name, s)
+    from tnrkit.jl_b200 import cft as cft_mod
+
+    assert cft_mod._sym_ok(s)               # sector-native path: no dense contraction is called
+    dense_calls = emu.calls.get("tnr_contract", 0)
+    grouped = emu.calls["tnr_gemm_grouped"]
     for u in (1, 2):
         got, ref = tk.cft_data(s, unitcell=u), o.cft_data(tw, unitcell=u)
         k = min(6, len(ref))
@@ -290,6 +295,7 @@ def test_emulated_cft_observables_match_oracle(tk, emu, name):
         assert abs(tk.ground_state_degeneracy(s, u) - o.ground_state_degeneracy(tw, u)) <= 1e-10
     assert np.abs(np.array(tk.gu_wen_ratio(s)) - np.array(o.gu_wen_ratio(tw))).max() <= 1e-10
     assert abs(tk.central_charge(s, 1.7) - o.central_charge(tw, 1.7)) <= 1e-10
+    assert emu.calls.get("tnr_contract", 0) == dense_calls and emu.calls["tnr_gemm_grouped"] > grouped
     # finalizer forms through run!: one entry per step plus the initial one
     s2 = getattr(tk, name)(tk.classical_ising(o.ising_bc + 0.01))
     data = tk.run(s2, tk.truncrank(8), tk.maxiter(3), tk.guwenratio_Finalizer, verbosity=0)

@@ -12,8 +12,11 @@ general (non-hermitian) `eig_full` on the chi^u x chi^u transfer matrix; that sp
 small matrix per call is taken with LAPACK on the host, like the reference does -- it is
 post-processing of a finished run, not part of `step!` / `finalize!`.
 
-Block-sparse schemes are densified first, as in `finalize_two_by_two` (eigenvalues of a
-block-diagonal matrix are the union of the block spectra, so the numbers are the same).
+Block-sparse schemes stay block-sparse: the same contractions run sector by sector
+(`sym_contract`, one grouped DMMA launch each) and only the chi^u x chi^u results leave the
+device (eigenvalues of a block-diagonal matrix are the union of the block spectra, so the numbers
+equal the dense ones).  `_dense_T` (host round trip of the whole tensor) is only the fallback for
+tensors whose ring legs are not dual to each other.
 """
 from __future__ import annotations
 
@@ -64,12 +67,59 @@ def _scalar(t: DeviceTensor) -> float:
     return float(t.to_numpy().reshape(-1)[0])
 
 
+# ---- block-sparse forms -------------------------------------------------------------------
+def _sym_ok(scheme) -> bool:
+    """Block-sparse scheme whose legs 1/4 and 2/3 are dual to each other (always the case for the
+    tensors TRG / BTRG / HOTRG / ATRG produce)."""
+    if not getattr(scheme, "sym", False):
+        return False
+    L = scheme.T.legs
+    return len(L) == 4 and all(L[i].sign == -L[j].sign and L[i].same_space(L[j])
+                               for i, j in ((0, 3), (1, 2)))
+
+
+def _sym_eye(T, i, j):
+    """delta on the legs (i, j) of T as a SymTensor that contracts with both."""
+    from .symmetric import Leg, SymTensor
+
+    li, lj = T.legs[i], T.legs[j]
+    legs = [Leg(li.dims, -li.sign), Leg(lj.dims, -lj.sign)]
+    blocks = {(q, q): DeviceTensor.from_numpy(np.eye(li.dims[q]), 1, T.ctx) for q in li.charges}
+    return SymTensor(T.N, legs, blocks, T.ctx)
+
+
+def _sym_unit_tensor(scheme):
+    T = scheme.T
+    if hasattr(scheme, "S1"):
+        from .symmetric import sym_clone
+
+        T = sym_clone(T).scale_leg(0, scheme.S2).scale_leg(1, scheme.S1)
+    return T
+
+
+def _sym_transfer_matrix(scheme, unitcell):
+    from .symmetric import sym_contract
+
+    T = _sym_unit_tensor(scheme)
+    rows, cols = "bcdefg"[:unitcell], "hijklm"[:unitcell]
+    R, lab = T, "a" + rows[0] + cols[0] + "z"
+    for i in range(1, unitcell):
+        new = "a" + rows[: i + 1] + cols[: i + 1] + "z"
+        R = sym_contract(R, lab.replace("z", "y"), T, "y" + rows[i] + cols[i] + "z", new)
+        lab = new
+    M = sym_contract(R, lab.replace("z", "y"), _sym_eye(T, 0, 3), "ay", rows + cols).to_dense()
+    n = math.prod(M.shape[:unitcell])
+    return M.reshape((n, -1), order="F")
+
+
 def transfer_matrix(scheme, unitcell: int = 1) -> np.ndarray:
     """ncon(fill(T, u), [[i, -i, -(i+u), i+1]..., last leg 4 -> 1]) as a matrix from the legs 2
     to the legs 3 (cft.jl:7-16, 280-295): a ring of u tensors along legs 1 / 4, contracted on the
     device; the chi^u x chi^u result is returned to the host."""
     if unitcell < 1 or unitcell > 6:
         raise ValueError("unitcell must be 1..6")
+    if _sym_ok(scheme):
+        return _sym_transfer_matrix(scheme, unitcell)
     T = _unit_tensor(scheme)
     rows = "bcdefg"[:unitcell]
     cols = "hijklm"[:unitcell]
@@ -101,6 +151,16 @@ def central_charge(scheme, n):
     """central_charge(scheme, n) -- cft.jl:256-260: M[-1;-2] := (T / n)[1 -1;-2 1],
     c = 6/pi log(sigma_max(M)); BTRG (cft.jl:262-269): M := T[1 -1;3 2] S1[3;-2] S2[2;1] / n.
     The largest singular value comes from the device SVD (`tnr_svd_trunc`, truncrank(1))."""
+    if _sym_ok(scheme):
+        from .symmetric import sym_clone, sym_contract, sym_svd_trunc
+
+        T = scheme.T
+        if hasattr(scheme, "S1"):
+            T = sym_clone(T).scale_leg(0, scheme.S2).scale_leg(2, scheme.S1)
+        M = sym_contract(T, "abcd", _sym_eye(T, 0, 3), "ad", "bc")
+        _, S, _, _ = sym_svd_trunc(M, 1, 1)
+        (s1,) = [float(v.to_numpy().reshape(-1)[0]) for v in S.values()]
+        return math.log(s1 / abs(n)) * 6 / math.pi
     T = _dense_T(scheme)
     if hasattr(scheme, "S1"):
         d = T.dims
@@ -126,6 +186,15 @@ def ground_state_degeneracy(scheme, unitcell: int = 1):
 def gu_wen_ratio(scheme):
     """gu_wen_ratio(scheme) -- cft.jl:374-383 (BTRG: 385-395):
     X1 = |T[1 2;2 1]|^2 / |T[1 2;2 3] T[3 4;4 1]|,  X2 = |T[1 2;2 1]|^2 / |T[1 2;3 4] T[4 3;2 1]|."""
+    if _sym_ok(scheme):
+        from .symmetric import sym_contract
+
+        T = _sym_unit_tensor(scheme)
+        M = sym_contract(T, "abcd", _sym_eye(T, 1, 2), "bc", "ad")    # T[a 2;2 d]
+        one = abs(np.trace(M.to_dense()))
+        x1 = abs(np.trace(sym_contract(M, "ac", M, "cb", "ab").to_dense()))
+        x2 = abs(np.trace(sym_contract(T, "abcd", T, "dcbe", "ae").to_dense()))
+        return one ** 2 / x1, one ** 2 / x2
     T = _unit_tensor(scheme)
     M = contract(T, "abcd", _eye(T.dims[1], T.ctx), "bc", "ad")       # T[a 2;2 d]
     one = abs(_scalar(contract(M, "ad", _eye(T.dims[0], T.ctx), "ad", "")))
