@@ -483,9 +483,15 @@ def hotrg3d_chunk_contract(Qk, Pk):
 
 
 def finalize_two_by_two(scheme):
-    """src/utility/finalize.jl:17-25 (2x2 unit-cell norm)."""
+    """src/utility/finalize.jl:17-25 (2x2 unit-cell norm); BTRG: finalize.jl:27-42,
+    T[11 1;9 8] S2[8;2] T[2 6;10 11] S1[3;6] T[7 10;3 12] S2[4;7] T[12 9;5 4] S1[5;1]."""
     T = scheme.T
-    n = abs(np.einsum("gaed,dbfg,cfbh,heac->", T, T, T, T, optimize=_OPT))
+    if isinstance(scheme, BTRG):
+        # labels 1..12 -> a..l
+        n = abs(np.einsum("kaih,hb,bfjk,cf,gjcl,dg,lied,ea->", T, scheme.S2, T, scheme.S1, T,
+                          scheme.S2, T, scheme.S1, optimize=_OPT))
+    else:
+        n = abs(np.einsum("gaed,dbfg,cfbh,heac->", T, T, T, T, optimize=_OPT))
     f = n ** 0.25
     scheme.T = T / f
     return f

@@ -75,3 +75,18 @@ def test_observable_finalizers_through_run(tk):
         tw.step(8)
         ref.append(o.finalize_central_charge(tw))
     assert np.abs(np.array(data) - np.array(ref)).max() <= 1e-9
+
+
+@pytest.mark.parametrize("sector", ["Z2", "Trivial"])
+@pytest.mark.parametrize("name", ["TRG", "BTRG", "HOTRG", "ATRG"])
+def test_two_by_two_finalizer_all_schemes(tk, name, sector):
+    """finalize_two_by_two! (finalize.jl:17-25; BTRG with bond weights: 27-42) through run!."""
+    T = tk.classical_ising() if sector == "Z2" else tk.classical_ising(tk.Trivial)
+    got = tk.run(getattr(tk, name)(T), tk.truncrank(8), tk.maxiter(4), tk.two_by_two_Finalizer,
+                 verbosity=0)
+    tw = getattr(o, name)(o.classical_ising())
+    ref = [o.finalize_two_by_two(tw)]
+    for _ in range(4):
+        tw.step(8)
+        ref.append(o.finalize_two_by_two(tw))
+    assert np.max(np.abs(np.array(got) - np.array(ref)) / np.abs(ref)) <= 1e-10

@@ -329,3 +329,28 @@ def test_emulated_cft_observables_dense_tensor(tk, emu):
         assert abs(tk.central_charge(s, 0.9) - o.central_charge(tw, 0.9)) <= 1e-10
     with pytest.raises(TypeError):
         tk.cft_data(tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=False))
+
+
+@pytest.mark.parametrize("name", ["TRG", "BTRG", "HOTRG", "ATRG"])
+def test_emulated_two_by_two_finalizer(tk, emu, name):
+    """finalize_two_by_two! (finalize.jl:17-25; BTRG with its bond weights: 27-42) through run!
+    on a block-sparse scheme, and on a dense scheme loaded with the same state."""
+    s = getattr(tk, name)(tk.classical_ising())
+    got = tk.run(s, tk.truncrank(8), tk.maxiter(4), tk.two_by_two_Finalizer, verbosity=0)
+    tw = getattr(o, name)(o.classical_ising())
+    ref = [o.finalize_two_by_two(tw)]
+    for _ in range(4):
+        tw.step(8)
+        ref.append(o.finalize_two_by_two(tw))
+    assert np.max(np.abs(np.array(got) - np.array(ref)) / np.abs(ref)) <= RTOL
+    if name in ("TRG", "BTRG"):
+        d = getattr(tk, name)(tk.classical_ising(tk.Trivial))
+        tw.T = 1.7 * tw.T
+        d.T = tk.DeviceTensor.from_numpy(tw.T, 2, emu)
+        if name == "BTRG":
+            d.S1 = tk.DeviceTensor.from_numpy(np.diag(tw.S1).copy(), 1, emu)
+            d.S2 = tk.DeviceTensor.from_numpy(np.diag(tw.S2).copy(), 1, emu)
+        want = o.finalize_two_by_two(tw)
+        assert abs(want - 1.7) <= 1e-9
+        assert abs(tk.finalize_two_by_two(d) - want) <= RTOL * want
+        assert np.abs(d.T.to_numpy() - tw.T).max() <= 1e-12 * np.abs(tw.T).max()

@@ -587,20 +587,53 @@ def beta_sweep(scheme_cls, model, betas, trscheme, criterion, **scheme_kwargs):
 def finalize_two_by_two(scheme):
     """finalize_two_by_two!(scheme::Union{TRG,ATRG,HOTRG}) -- src/utility/finalize.jl:17-25:
     n = |T[7 1;5 4] T[4 2;6 7] T[3 6;2 8] T[8 5;1 3]|, T /= n^(1/4), returns n^(1/4).
-    Dense tensors only (block-sparse schemes are densified on the fly)."""
-    import ctypes as C_
-
+    BTRG (finalize.jl:27-42): the same ring of four tensors with the diagonal bond weights S2 on
+    the bonds 8-2 and 4-7 and S1 on the bonds 3-6 and 5-1; they are absorbed into the legs of
+    three of the four tensors (`tnr_axis_scale`).  Block-sparse schemes run the contractions
+    sector by sector; only a chi x chi matrix is traced on the host."""
     from .tensor import contract as _contract
 
-    T = scheme.T
-    if getattr(scheme, "sym", False):
-        T = DeviceTensor.from_numpy(T.to_dense(), 2, scheme.ctx)
-    # labels: 7=g 1=a 5=e 4=d 2=b 6=f 3=c 8=h
-    X = _contract(T, "gaed", T, "dbfg", "aebf")      # sum over d, g
-    Y = _contract(T, "cfbh", T, "heac", "fbea")      # sum over c, h
-    n = abs(float(_contract(X, "aebf", Y, "fbea", "").to_numpy().reshape(-1)[0]))
+    sym = getattr(scheme, "sym", False)
+    weighted = hasattr(scheme, "S1")
+    if sym:
+        from .symmetric import sym_clone, sym_contract
+
+        T = scheme.T
+        L = T.legs
+        if not all(L[i].sign == -L[j].sign and L[i].same_space(L[j]) for i, j in ((0, 3), (1, 2))):
+            raise ValueError("finalize_two_by_two: legs 1/4 and 2/3 must be dual to each other")
+
+        def w(legs):
+            if not weighted or not legs:
+                return T
+            W = sym_clone(T)
+            for ax in legs:
+                W.scale_leg(ax, scheme.S2 if ax == 0 else scheme.S1)
+            return W
+
+        X = sym_contract(w((1,)), "gaed", w((0, 1)), "dbfg", "aebf")
+        Y = sym_contract(w((0,)), "cfbh", T, "heac", "fbea")
+        n = abs(float(np.trace(sym_contract(X, "aebf", Y, "fbxa", "ex").to_dense())))
+    else:
+        T = scheme.T
+        d = T.dims
+
+        def w(legs):
+            if not weighted or not legs:
+                return T
+            W = T.clone()
+            for ax in legs:
+                S = scheme.S2 if ax == 0 else scheme.S1
+                W.ctx.call("tnr_axis_scale", W.ptr, math.prod(d[:ax]), d[ax],
+                           math.prod(d[ax + 1:]), S.ptr, 0, 0.0)
+            return W
+
+        # labels: 7=g 1=a 5=e 4=d 2=b 6=f 3=c 8=h
+        X = _contract(w((1,)), "gaed", w((0, 1)), "dbfg", "aebf")      # sum over d, g
+        Y = _contract(w((0,)), "cfbh", T, "heac", "fbea")              # sum over c, h
+        n = abs(float(_contract(X, "aebf", Y, "fbea", "").to_numpy().reshape(-1)[0]))
     f = n ** 0.25
-    if getattr(scheme, "sym", False):
+    if sym:
         scheme.T.scale(1.0 / f)
     else:
         scheme.ctx.call("tnr_scale", scheme.T.ptr, scheme.T.size, 1.0 / f)
