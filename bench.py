@@ -236,6 +236,8 @@ def run_gpu(args):
     ctx = tk.default_context()
     if args.engine == "ozaki":
         ctx.set_option("ozaki", args.ozaki_planes)
+    elif args.engine == "ozaki_crt":
+        ctx.set_option("ozaki_crt", args.crt_moduli)
     chi = args.chi
     peak = measure_fp64_peak(torch, dev) if rank == 0 else None
 
@@ -317,7 +319,10 @@ def run_gpu(args):
             "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.engine == "dmma" else
-            f"f64 emulated by {args.ozaki_planes} int8 digit planes (Ozaki scheme, tcgen05 kind::i8)",
+            (f"f64 emulated by {args.ozaki_planes} int8 digit planes (Ozaki scheme, tcgen05 kind::i8)"
+             if args.engine == "ozaki" else
+             f"f64 emulated by int8 residue products modulo {args.crt_moduli} coprime moduli "
+             f"(CRT / Ozaki scheme II, tcgen05 kind::i8)"),
             "data": "synthetic",
             "config": {
                 "engine": args.engine,
@@ -388,7 +393,8 @@ def main():
     ap.add_argument("--chi", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--engine", default="dmma", choices=["dmma", "ozaki"],
+    ap.add_argument("--crt-moduli", type=int, default=16)
+    ap.add_argument("--engine", default="dmma", choices=["dmma", "ozaki", "ozaki_crt"],
                     help="dmma: FP64 tensor cores (default, the measured configuration); ozaki: "
                          "EXPERIMENTAL FP64 emulation of the chunk GEMM on the INT8 tensor cores")
     ap.add_argument("--ozaki-planes", type=int, default=8)

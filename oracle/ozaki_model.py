@@ -45,3 +45,49 @@ def multiply(A, B, slices=8):
         assert np.abs(acc).max() < 2 ** 31
         C = C + acc.astype(np.float64) * (np.ldexp(1.0, -12 - 7 * t) * sa[:, None] * sb[None, :])
     return C
+
+
+# ---- CRT variant ("ozaki_crt", csrc/crt_math.cuh + ozaki_crt_split_kernel / ozaki_tile_kernel<true>
+# / ozaki_crt_reconstruct_kernel): bit-level model with exact Python integers for the CRT -----------
+CRT_MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181]
+
+
+def crt_bits(nmod, klog=14):
+    import math
+
+    P = math.prod(CRT_MODULI[:nmod])
+    return min(53, (P.bit_length() - 2 - klog) // 2)
+
+
+def crt_split(X, nmod):
+    """X: rows x K.  residues[nmod][rows][K] in [-p/2, p/2) and scale[rows] = 2^(e - bits)."""
+    bits = crt_bits(nmod)
+    amax = np.abs(X).max(axis=1)
+    e = np.where(amax > 0, np.frexp(amax)[1], 0)
+    Xi = np.rint(np.ldexp(X, (bits - e)[:, None]))
+    Xo = np.array([[int(v) for v in row] for row in Xi], dtype=object)
+    res = []
+    for p in CRT_MODULI[:nmod]:
+        h = p // 2 if p % 2 == 0 else (p - 1) // 2
+        res.append(np.array([[((v + h) % p) - h for v in row] for row in Xo], dtype=np.int64))
+    return res, np.ldexp(1.0, e - bits), Xo
+
+
+def multiply_crt(A, B, nmod=16):
+    """C = A B^T as the CRT engine computes it (the reconstruction with exact integers; the FP64
+    limb form of csrc/crt_math.cuh is checked against the same integers in
+    tests/test_crt_math_host.py)."""
+    import math
+
+    ra, sa, _ = crt_split(A, nmod)
+    rb, sb, _ = crt_split(B, nmod)
+    ms = CRT_MODULI[:nmod]
+    P = math.prod(ms)
+    tot = np.zeros((A.shape[0], B.shape[0]), dtype=object)
+    for i, p in enumerate(ms):
+        acc = ra[i] @ rb[i].T                    # int32 range on the GPU
+        assert np.abs(acc).max() < 2 ** 31
+        w = (P // p) * pow(P // p, -1, p)
+        tot = tot + (acc % p).astype(object) * w
+    lift = np.vectorize(lambda x: ((x + P // 2) % P) - P // 2)(tot)
+    return np.array(lift, dtype=np.float64) * sa[:, None] * sb[None, :]

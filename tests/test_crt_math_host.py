@@ -95,3 +95,25 @@ def test_crt_host_arithmetic_is_exact(shim, nmod, K):
     mag = np.abs(A).astype(np.longdouble) @ np.abs(B.T).astype(np.longdouble)
     err = float(np.max(np.abs(Cemu - ref) / np.where(mag > 0, mag, 1)))
     assert err <= {14: 2e-13, 16: 3e-16, 18: 3e-16}[nmod], err
+
+
+def test_bit_level_model_agrees_with_host_arithmetic(shim):
+    """oracle/ozaki_model.py: multiply_crt (exact-integer CRT) == the FP64-limb pipeline of
+    crt_math.cuh on the same operands, to the final rounding."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ozaki_model
+
+    rng = np.random.default_rng(5)
+    m, n, K, nmod = 4, 3, 2048, 16
+    A = rng.standard_normal((m, K)) * np.exp(rng.uniform(-6, 6, size=(m, K)))
+    B = rng.standard_normal((n, K))
+    want = ozaki_model.multiply_crt(A, B, nmod)
+    ra, sa, _ = ozaki_model.crt_split(A, nmod)
+    rb, sb, _ = ozaki_model.crt_split(B, nmod)
+    acc = np.ascontiguousarray(np.stack([ra[i] @ rb[i].T for i in range(nmod)]).astype(np.int32)
+                               ).reshape(nmod, m * n)
+    out = np.zeros(m * n)
+    assert shim.crt_host_reconstruct(acc.ctypes.data_as(C.c_void_p), C.c_longlong(m * n), nmod,
+                                     out.ctypes.data_as(C.c_void_p)) == 0
+    got = out.reshape(m, n) * sa[:, None] * sb[None, :]
+    assert np.max(np.abs(got - want) / np.abs(want)) <= 2.3e-16

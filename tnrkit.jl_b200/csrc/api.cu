@@ -141,6 +141,10 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             TNR_CHECK(value == 0 || (value >= 4 && value <= 10), "ozaki: 0 (off) or 4..10 digit planes");
             ctx->c.ozaki_slices = (int)value;
         }
+        else if (std::strcmp(key, "ozaki_crt") == 0) {
+            TNR_CHECK(value == 0 || (value >= 14 && value <= 18), "ozaki_crt: 0 (off) or 14..18 moduli");
+            ctx->c.ozaki_crt = (int)value;
+        }
         else if (std::strcmp(key, "permute_tile") == 0) {
             TNR_CHECK(value == 32 || value == 48 || value == 64 || value == 96,
                       "permute_tile: 32, 48, 64 or 96 (default)");
@@ -263,7 +267,8 @@ int tnr_gemm_ozaki(tnr_context* ctx, int m, int n, int k, const double* A, int64
     if (!ctx) return 1;
     return guard(ctx, [&] {
         Context* c = &ctx->c;
-        TNR_CHECK(c->ozaki_slices > 0, "gemm_ozaki: enable with tnr_set_option(ctx, \"ozaki\", 8)");
+        TNR_CHECK(c->ozaki_slices > 0 || c->ozaki_crt > 0,
+                  "gemm_ozaki: enable with tnr_set_option(ctx, \"ozaki\", 8) or (ctx, \"ozaki_crt\", 16)");
         TNR_CHECK(ozaki_applicable(c, m, n, k),
                   "gemm_ozaki: needs m, n, k >= 512, k % 16 == 0 and slices * k * 4096 < 2^31");
         OzakiOperand a = ozaki_split(c, A, lda, m, k);

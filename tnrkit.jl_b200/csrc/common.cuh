@@ -59,6 +59,7 @@ struct Context {
     bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
     int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
     int permute_unroll = 1;  // 2 | 4: permute kernels with several loads in flight per thread (opt-in)
+    int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
     double timed_flops = 0.0;
@@ -107,7 +108,8 @@ struct OzakiOperand {        // int8 digit planes of the rows of a K-major FP64 
     int8_t* planes = nullptr;  // [slices][rows][K]
     double* scale = nullptr;   // [rows] power-of-two row scale
     long long rows = 0, K = 0;
-    int slices = 0;
+    int slices = 0;            // digit planes, or moduli when crt
+    bool crt = false;          // planes are residues modulo the first `slices` CRT moduli
 };
 bool ozaki_applicable(const Context* ctx, long long m, long long n, long long k);
 OzakiOperand ozaki_split(Context* ctx, const double* X, long long ld, long long rows, long long K);

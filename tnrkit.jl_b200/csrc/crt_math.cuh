@@ -40,6 +40,18 @@ TNR_HD int crt_acc_residue(int v, int p, double inv_p) {
     return r;
 }
 
+// quotient q = rint(x / P) from the leading limb sums, then Horner over the corrected limbs;
+// NLV (number of limbs incl. one spare) is a template parameter so that S stays in registers
+template <int NLV>
+TNR_HD double crt_finish(const double* S, const CrtTable& t) {
+    const double top = S[NLV - 1] * 4294967296.0 + S[NLV - 2] + S[NLV - 3] * (1.0 / 4294967296.0);
+    const double q = rint(top / t.Pscaled);      // |q| <= 256 N
+    double out = 0.0;
+#pragma unroll
+    for (int j = NLV - 1; j >= 0; --j) out = out * 4294967296.0 + (S[j] - q * t.PL[j]);
+    return out;
+}
+
 // symmetric lift of sum_i res[i] w_i mod P as a double; res[i] in [0, p_i), stride between
 // consecutive moduli = `stride` bytes.  Every product and sum below is exact in FP64 (limb sums
 // < 2^45); only the final Horner sum rounds (relative 2^-53 of the value itself).
@@ -52,14 +64,7 @@ TNR_HD double crt_reconstruct(const unsigned char* res, long long stride, const 
 #pragma unroll
         for (int j = 0; j < CRT_NL; ++j) S[j] += r * t.W[i][j];
     }
-    const int nl = t.nl;
-    const double top = S[nl - 1] * 4294967296.0 + S[nl - 2] + S[nl - 3] * (1.0 / 4294967296.0);
-    const double q = rint(top / t.Pscaled);      // quotient x / P, |q| <= 256 N
-    double out = 0.0;
-#pragma unroll
-    for (int j = CRT_NL - 1; j >= 0; --j)
-        if (j < nl) out = out * 4294967296.0 + (S[j] - q * t.PL[j]);
-    return out;
+    return t.nl == 5 ? crt_finish<5>(S, t) : crt_finish<6>(S, t);
 }
 
 }  // namespace tnr

@@ -27,9 +27,13 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "crt_math.cuh"
 
 namespace tnr {
 namespace {
+
+// constants of the CRT variant (one table per launch configuration, set by ozaki_crt_table)
+__constant__ CrtTable c_crt;
 
 constexpr int OBM = 128, OBN = 256, OBK = 128, OSTAGES = 4;
 constexpr int OA_BYTES = OBM * OBK, OB_BYTES = OBN * OBK, OSTAGE_BYTES = OA_BYTES + OB_BYTES;
@@ -101,12 +105,21 @@ struct OzakiParams {
     const double* scaleB;  // 2^e per row of B^T
     int M, N, K;
     int S;         // digit planes; groups t = S-1 .. 0, group t = pairs (i, t - i), weight 2^(-12-7t)
+                   // CRT variant: number of moduli; group g = the single pair (g, g)
+    unsigned char* R;        // CRT variant: residues [S][N][ldr] of the accumulators, in [0, p_g)
+    long long ldr;           // rows of R (>= M)
 };
 
 // One CTA per 128 x 256 output tile.  All S accumulation groups of the tile run inside one
 // launch: the MMA thread alternates between two 256-column TMEM accumulators, the four epilogue
 // warps drain accumulator g (convert, scale, accumulate into FP64 C) while the MMAs of group
 // g + 1 are already running.
+//
+// CRT = true (option "ozaki_crt"): the planes are the symmetric residues of the scaled operands
+// modulo p_0..p_{S-1}; group g is the single product (plane g) x (plane g), and the epilogue
+// stores the residue of the INT32 accumulator mod p_g as one byte per element
+// (ozaki_crt_reconstruct_kernel turns the S residues into the FP64 result afterwards).
+template <bool CRT>
 __global__ void __launch_bounds__(OTHREADS, 1)
 ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const OzakiParams p) {
@@ -162,8 +175,8 @@ ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             int it = 0;
             for (int g = 0; g < S; ++g) {
                 const int t = S - 1 - g;
-                for (int i = 0; i <= t; ++i) {
-                    const int j = t - i;
+                for (int i = CRT ? g : 0; i <= (CRT ? g : t); ++i) {
+                    const int j = CRT ? g : t - i;
                     for (int kb = 0; kb < KB; ++kb, ++it) {
                         int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
                         o_mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -187,7 +200,7 @@ ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 o_mbar_wait(tempty0 + 8 * buf, ((g >> 1) & 1) ^ 1);  // accumulator drained
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned acc = tmem_base + (unsigned)(buf * OTMEM_COLS);
-                const int nblk = KB * (t + 1);
+                const int nblk = CRT ? KB : KB * (t + 1);
                 for (int b = 0; b < nblk; ++b, ++it) {
                     int s = it % OSTAGES, ph = (it / OSTAGES) & 1;
                     o_mbar_wait(full0 + 8 * s, ph);
@@ -228,6 +241,18 @@ ozaki_tile_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                       "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if constexpr (CRT) {
+                    if (row < p.M) {
+                        const int pg = c_crt.p[g];
+                        const double ig = c_crt.inv_p[g];
+                        unsigned char* rp = p.R + ((long long)g * p.N + (n0 + c0)) * p.ldr + row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < p.N)
+                                rp[(long long)j * p.ldr] =
+                                    (unsigned char)crt_acc_residue((int)v[j], pg, ig);
+                    }
+                } else
                 if (row < p.M) {
                     // all loads of the old C values are issued before the first store, so the
                     // 32 read-modify-writes overlap instead of paying 32 global latencies in turn
@@ -309,6 +334,61 @@ __global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restri
     }
 }
 
+// ---- CRT variant: symmetric residues of the scaled rows, one int8 plane per modulus ----
+// X as above; planes[i][r][k] = (rint(x 2^(bits-e)) mod p_i) in [-p_i/2, p_i/2),
+// scale[r] = 2^(e - bits) so that C = (integer dot product) * scale_row * scale_col.
+__global__ void __launch_bounds__(256) ozaki_crt_split_kernel(const double* __restrict__ X,
+                                                              long long ld, int K,
+                                                              int8_t* __restrict__ planes,
+                                                              long long plane_stride,
+                                                              double* __restrict__ scale) {
+    const int r = blockIdx.x;
+    const double* x = X + (long long)r * ld;
+    __shared__ double red[256];
+    double amax = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) amax = fmax(amax, fabs(x[k]));
+    red[threadIdx.x] = amax;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    amax = red[0];
+    int e = 0;
+    if (amax > 0.0 && isfinite(amax)) e = ilogb(amax) + 1;  // amax * 2^-e in [0.5, 1)
+    const int bits = c_crt.bits, nmod = c_crt.nmod;
+    if (threadIdx.x == 0) scale[r] = ldexp(1.0, e - bits);
+    int8_t* out = planes + (long long)r * K;
+    // 8 consecutive k per thread: one 64-byte read, one packed 8-byte store per residue plane
+    for (int k8 = threadIdx.x * 8; k8 < K; k8 += 256 * 8) {
+        double xi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xi[u] = rint(ldexp(x[k8 + u], bits - e));   // |xi| <= 2^bits
+        for (int i = 0; i < nmod; ++i) {
+            const int pi = c_crt.p[i];
+            const double ii = c_crt.inv_p[i];
+            unsigned long long pack = 0ULL;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                pack |= (unsigned long long)(unsigned char)(signed char)crt_residue(xi[u], pi, ii)
+                        << (8 * u);
+            *reinterpret_cast<unsigned long long*>(out + (long long)i * plane_stride + k8) = pack;
+        }
+    }
+}
+
+// C[col*ldc + row] = crt_reconstruct(residues of element (row, col)) * scaleA[row] * scaleB[col]
+__global__ void __launch_bounds__(256) ozaki_crt_reconstruct_kernel(
+    const unsigned char* __restrict__ R, long long ldr, int M, int N,
+    const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C,
+    long long ldc) {
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    const int col = blockIdx.y;
+    if (row >= M) return;
+    const double v = crt_reconstruct(R + (long long)col * ldr + row, (long long)N * ldr, c_crt);
+    C[(long long)col * ldc + row] = v * (scaleA[row] * scaleB[col]);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -345,14 +425,37 @@ bool make_plane_map(CUtensorMap* map, const int8_t* base, long long rows, long l
 
 bool ozaki_applicable(const Context* ctx, long long m, long long n, long long k) {
     // exact int32 accumulation needs (slices) * K * 64^2 < 2^31; TMA needs 16-byte row strides
+    if (ctx->ozaki_crt > 0)   // residues |a|, |b| <= 128: K * 2^14 < 2^31; P covers K <= 2^14
+        return (k % 16) == 0 && m >= 512 && n >= 512 && k >= 512 && k <= 16384;
     return ctx->ozaki_slices >= 2 && (k % 16) == 0 && m >= 512 && n >= 512 && k >= 512 &&
            (double)ctx->ozaki_slices * (double)k * 4096.0 < 2147483648.0;
+}
+
+// uploads the table for `nmod` moduli into constant memory (stream-ordered; only when it changes)
+static void ozaki_crt_table(Context* ctx, int nmod) {
+    static int loaded = 0;
+    if (loaded == nmod) return;
+    TNR_CUDA(cudaMemcpyToSymbolAsync(c_crt, &CRT_TABLES[nmod - CRT_MIN_MOD], sizeof(CrtTable), 0,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    loaded = nmod;
 }
 
 OzakiOperand ozaki_split(Context* ctx, const double* X, long long ld, long long rows, long long K) {
     OzakiOperand o;
     o.rows = rows;
     o.K = K;
+    if (ctx->ozaki_crt > 0) {
+        o.slices = ctx->ozaki_crt;
+        o.crt = true;
+        ozaki_crt_table(ctx, o.slices);
+        TNR_CUDA(cudaMallocAsync((void**)&o.planes, (size_t)o.slices * rows * K, ctx->stream));
+        o.scale = dalloc(ctx, rows);
+        ozaki_crt_split_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(X, ld, (int)K, o.planes,
+                                                                       rows * K, o.scale);
+        TNR_CUDA(cudaGetLastError());
+        ctx->ctr.launches++;
+        return o;
+    }
     o.slices = ctx->ozaki_slices;
     TNR_CUDA(cudaMallocAsync((void**)&o.planes, (size_t)o.slices * rows * K, ctx->stream));
     o.scale = dalloc(ctx, rows);
@@ -373,15 +476,17 @@ void ozaki_free(Context* ctx, OzakiOperand& o) {
 // C(m x n, ldc) = A^T B from the digit planes of A^T (m rows) and B^T (n rows)
 void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, double* C,
                     long long ldc) {
-    TNR_CHECK(A.K == B.K && A.slices == B.slices, "ozaki_multiply: operand mismatch");
+    TNR_CHECK(A.K == B.K && A.slices == B.slices && A.crt == B.crt, "ozaki_multiply: operand mismatch");
     CUtensorMap mapA, mapB;
     TNR_CHECK(make_plane_map(&mapA, A.planes, A.rows, A.K, A.slices, OBM) &&
                   make_plane_map(&mapB, B.planes, B.rows, B.K, B.slices, OBN),
               "ozaki_multiply: tensor map encoding failed");
     static bool configured = false;
     if (!configured) {
-        TNR_CUDA(cudaFuncSetAttribute(ozaki_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)OSMEM));
+        TNR_CUDA(cudaFuncSetAttribute(ozaki_tile_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OSMEM));
+        TNR_CUDA(cudaFuncSetAttribute(ozaki_tile_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OSMEM));
         configured = true;
     }
     dim3 grid((unsigned)(((A.rows + OBM - 1) / OBM) * ((B.rows + OBN - 1) / OBN)));
@@ -390,8 +495,24 @@ void ozaki_multiply(Context* ctx, const OzakiOperand& A, const OzakiOperand& B, 
     p.scaleA = A.scale; p.scaleB = B.scale;
     p.M = (int)A.rows; p.N = (int)B.rows; p.K = (int)A.K;
     p.S = A.slices;
-    ozaki_tile_kernel<<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
-    TNR_CUDA(cudaGetLastError());
+    p.R = nullptr; p.ldr = 0;
+    if (A.crt) {
+        // residues of the accumulators: S bytes per element, reconstructed by a second kernel
+        ozaki_crt_table(ctx, A.slices);
+        p.ldr = A.rows;
+        TNR_CUDA(cudaMallocAsync((void**)&p.R, (size_t)A.slices * A.rows * B.rows, ctx->stream));
+        ozaki_tile_kernel<true><<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
+        TNR_CUDA(cudaGetLastError());
+        dim3 rg((unsigned)((A.rows + 255) / 256), (unsigned)B.rows);
+        ozaki_crt_reconstruct_kernel<<<rg, 256, 0, ctx->stream>>>(p.R, p.ldr, p.M, p.N, A.scale,
+                                                                 B.scale, C, ldc);
+        TNR_CUDA(cudaGetLastError());
+        TNR_CUDA(cudaFreeAsync(p.R, ctx->stream));
+        ctx->ctr.launches++;
+    } else {
+        ozaki_tile_kernel<false><<<grid, OTHREADS, OSMEM, ctx->stream>>>(mapA, mapB, p);
+        TNR_CUDA(cudaGetLastError());
+    }
     ctx->ctr.launches++;
     ctx->ctr.ozaki_launches++;
     ctx->ctr.gemm_flops += 2.0 * A.rows * B.rows * (double)A.K;
