@@ -1,0 +1,67 @@
+// Host build (g++) of csrc/permute_plan.cuh for tests/test_permute_host.py -- test infrastructure.
+// Runs the planner of strided_copy and, for the tiled case, the two per-thread phases of
+// copy_tiled_mlp_kernel<U> block by block, thread by thread (phase 1 for all 256 threads, then
+// phase 2: the __syncthreads() of the kernel).
+#include <cstring>
+#include <vector>
+
+#include "../tnrkit.jl_b200/csrc/permute_plan.cuh"
+
+using namespace tnr;
+
+extern "C" {
+// TensorKit-style permute: new leg k = old leg perm[k]; column-major data.
+// Returns the plan kind (1 flat, 2 rows, 3 tiled) or a negative number on error;
+// info[0..5] = TI1*TI2, TJ1*TJ2, blocks, smem bytes, pitch, merged outer rank.
+int permute_host(const double* src, double* dst, int rank, const long long* dims, const int* perm,
+                 int unroll, int tile, long long* info) {
+    long long sst[16], dims_out[16], dst_st[16], src_st_for_out[16];
+    long long s = 1;
+    for (int i = 0; i < rank; ++i) { sst[i] = s; s *= dims[i]; }
+    long long d = 1;
+    for (int k = 0; k < rank; ++k) {
+        int q = perm[k];
+        dims_out[k] = dims[q];
+        dst_st[k] = d;
+        d *= dims[q];
+        src_st_for_out[k] = sst[q];
+    }
+    CopyPlan plan = plan_strided_copy(rank, dims_out, src_st_for_out, dst_st, tile);
+    if (plan.error) return -1;
+    const CopyParams& p = plan.p;
+    info[0] = (long long)p.TI1 * p.TI2; info[1] = (long long)p.TJ1 * p.TJ2;
+    info[2] = plan.blocks; info[3] = (long long)plan.smem; info[4] = p.pitch; info[5] = p.rank;
+    if (plan.total == 0) return 0;
+    if (plan.kind == COPY_FLAT) {
+        std::memcpy(dst, src, sizeof(double) * (size_t)plan.total);
+    } else if (plan.kind == COPY_ROWS) {
+        // the arithmetic of copy_rows_kernel, one "thread" per element
+        for (long long idx = 0; idx < p.total; ++idx) {
+            long long i = idx % p.ni, rest = idx / p.ni;
+            long long soff = i * p.si_s, doff = i * p.si_d;
+            for (int dd = 0; dd < p.rank; ++dd) {
+                long long k = rest % p.dims[dd];
+                rest /= p.dims[dd];
+                soff += k * p.ss[dd];
+                doff += k * p.ds[dd];
+            }
+            dst[doff] = src[soff];
+        }
+    } else {
+        if (p.TI1 * p.TI2 > 96 || p.TJ1 * p.TJ2 > 96) return -2;   // the kernel's precondition
+        std::vector<double> tile_buf(plan.smem / sizeof(double));
+        for (long long b = 0; b < plan.blocks; ++b) {
+            // poison the tile: a read of an element the read phase did not write shows up
+            std::fill(tile_buf.begin(), tile_buf.end(), -12345.678);
+            TileGeom g = tile_geometry(src, dst, p, b);
+            for (int tid = 0; tid < 256; ++tid) {
+                if (unroll >= 4) tile_read_phase<4>(g, p, tile_buf.data(), tid);
+                else if (unroll == 2) tile_read_phase<2>(g, p, tile_buf.data(), tid);
+                else tile_read_phase<1>(g, p, tile_buf.data(), tid);
+            }
+            for (int tid = 0; tid < 256; ++tid) tile_write_phase(g, p, tile_buf.data(), tid);
+        }
+    }
+    return (int)plan.kind;
+}
+}

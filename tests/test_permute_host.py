@@ -1,0 +1,66 @@
+"""Host check (g++, no GPU) of the index arithmetic of the permute path: the planner of
+`strided_copy` (flat / rows / tiled decision, merged index groups, composite tiles -- the code
+the default kernels run on) and the per-thread read / write phases of the opt-in
+copy_tiled_mlp_kernel<U> (`tnrkit.jl_b200/csrc/permute_plan.cuh`), executed block by block and
+thread by thread on the CPU against numpy.transpose.  Bit exact: pure data movement."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [
+    ((5,), (0,)), ((4, 7), (1, 0)), ((33, 65), (1, 0)), ((3, 4, 5), (2, 0, 1)),
+    ((2, 3, 4, 5), (1, 3, 0, 2)), ((6, 5, 4, 3, 2, 7), (5, 3, 1, 2, 0, 4)),
+    ((4, 4, 8, 8, 8, 8), (0, 1, 3, 2, 5, 4)), ((8, 8, 8, 8, 8, 8), (1, 3, 5, 0, 2, 4)),
+    ((24, 24, 24), (2, 1, 0)), ((1, 9, 1, 4), (3, 2, 1, 0)), ((40, 3, 40), (0, 2, 1)),
+    ((12,) * 6, (5, 3, 1, 2, 0, 4)), ((12,) * 6, (0, 5, 4, 3, 1, 2)), ((10, 7, 6, 9), (0, 3, 2, 1)),
+    ((100, 130), (1, 0)), ((97, 101), (1, 0)), ((50, 2, 50), (2, 1, 0)), ((200, 3, 5), (1, 2, 0)),
+    ((24, 24, 24, 24), (3, 2, 1, 0)), ((16, 6, 16, 6), (2, 3, 0, 1)), ((7, 5, 3, 2, 4, 6), (3, 1, 5, 0, 4, 2)),
+    ((24,) * 4 + (3, 2), (5, 3, 1, 2, 0, 4)),
+]
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("perm") / "libpermute_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "tests", "permute_host_shim.cpp")], check=True)
+    return C.CDLL(so)
+
+
+def _run(shim, a, perm, unroll, tile):
+    dims = a.shape
+    flat = np.ascontiguousarray(np.transpose(a).reshape(-1))          # column-major data
+    out = np.full(flat.size, np.nan)
+    info = (C.c_longlong * 6)()
+    kind = shim.permute_host(flat.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                             len(dims), (C.c_longlong * len(dims))(*dims),
+                             (C.c_int * len(perm))(*perm), unroll, tile, info)
+    od = tuple(dims[p] for p in perm)
+    return kind, np.transpose(out.reshape(tuple(reversed(od)))), list(info)
+
+
+@pytest.mark.parametrize("unroll,tile", [(1, 96), (2, 96), (4, 96), (4, 64), (2, 48), (4, 32)])
+@pytest.mark.parametrize("dims,perm", CASES)
+def test_planner_and_tiled_phases_on_host(shim, dims, perm, unroll, tile):
+    rng = np.random.default_rng(len(dims) * 10 + tile)
+    a = rng.standard_normal(dims)
+    kind, got, info = _run(shim, a, perm, unroll, tile)
+    assert kind in (1, 2, 3), kind
+    assert np.array_equal(got, np.transpose(a, perm))
+    if kind == 3:
+        assert info[0] <= tile and info[1] <= tile and info[4] % 2 == 1
+        assert info[3] <= 100 * 1024          # the dynamic shared memory the kernels opt in to
+
+
+def test_chi24_rotation_plan(shim):
+    """The permutation of hotrg3d.jl:134 at a reduced but structurally identical size (legs of 24
+    on the four tile legs): composite 96 x 96 tiles, 768-byte runs on both sides."""
+    a = np.random.default_rng(0).standard_normal((24, 24, 2, 3, 24, 24))
+    kind, got, info = _run(shim, a, (5, 3, 1, 2, 0, 4), 4, 96)
+    assert np.array_equal(got, np.transpose(a, (5, 3, 1, 2, 0, 4)))
+    assert kind == 3

@@ -11,6 +11,7 @@ for f in gemm_dmma gemm_tma gemm_ozaki permute elementwise jacobi tensor_ops sch
   if [ ! -f "$HERE/.obj/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/.obj/$f.o" ] || \
      [ "$HERE/common.cuh" -nt "$HERE/.obj/$f.o" ] || [ "$HERE/tensor.hpp" -nt "$HERE/.obj/$f.o" ] || \
      [ "$HERE/schemes.hpp" -nt "$HERE/.obj/$f.o" ] || [ "$HERE/crt_math.cuh" -nt "$HERE/.obj/$f.o" ] || \
+     [ "$HERE/permute_plan.cuh" -nt "$HERE/.obj/$f.o" ] || \
      [ "$HERE/crt_tables.inc" -nt "$HERE/.obj/$f.o" ] || [ "$HERE/../../include/tnrcuda.h" -nt "$HERE/.obj/$f.o" ]; then
     $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/.obj/$f.o" &
     pids+=($!)

@@ -13,29 +13,10 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "permute_plan.cuh"
 
 namespace tnr {
 namespace {
-
-constexpr int MAXR = 8;
-
-struct CopyParams {
-    int rank;                // number of "outer" dims (excluding tile dims for the tiled kernel)
-    long long dims[MAXR];
-    long long ss[MAXR];
-    long long ds[MAXR];
-    // row kernel: inner dim
-    long long ni, si_s, si_d;
-    long long total;
-    // tiled kernel: composite source-contiguous index i' = (i1, i2) and composite
-    // destination-contiguous index j' = (j1, j2)
-    long long n_i1, n_i2, n_j1, n_j2;          // full extents
-    long long s_i1, d_i1, d_i2, s_i2;          // strides of i1 / i2 (src, dst)
-    long long d_j1, s_j1, s_j2, d_j2;          // strides of j1 / j2
-    int TI1, TI2, TJ1, TJ2;                    // tile extents
-    long long tiles_i1, tiles_i2, tiles_j1, tiles_j2;
-    int pitch;
-};
 
 // Tile = (i1 x i2) x (j1 x j2): reads run along the source-contiguous composite i', writes along
 // the destination-contiguous composite j' (e.g. 96-element = 768-byte runs on both sides for
@@ -112,76 +93,10 @@ __global__ void __launch_bounds__(256) copy_tiled_mlp_kernel(const double* __res
                                                              double* __restrict__ dst,
                                                              const CopyParams p) {
     extern __shared__ double tile[];  // [TJ1*TJ2][pitch]
-    long long bid = blockIdx.x;
-    long long t_i1 = bid % p.tiles_i1; bid /= p.tiles_i1;
-    long long t_i2 = bid % p.tiles_i2; bid /= p.tiles_i2;
-    long long t_j1 = bid % p.tiles_j1; bid /= p.tiles_j1;
-    long long t_j2 = bid % p.tiles_j2; bid /= p.tiles_j2;
-    long long soff = 0, doff = 0;
-#pragma unroll
-    for (int d = 0; d < MAXR; ++d) {
-        if (d < p.rank) {
-            long long i = bid % p.dims[d];
-            bid /= p.dims[d];
-            soff += i * p.ss[d];
-            doff += i * p.ds[d];
-        }
-    }
-    const long long i10 = t_i1 * p.TI1, i20 = t_i2 * p.TI2, j10 = t_j1 * p.TJ1, j20 = t_j2 * p.TJ2;
-    const int ti1 = (int)min((long long)p.TI1, p.n_i1 - i10);
-    const int ti2 = (int)min((long long)p.TI2, p.n_i2 - i20);
-    const int tj1 = (int)min((long long)p.TJ1, p.n_j1 - j10);
-    const int tj2 = (int)min((long long)p.TJ2, p.n_j2 - j20);
-    const int ci = ti1 * ti2, cj = tj1 * tj2;   // composite extents of this tile (each <= 96)
-    const double* sp = src + soff + i10 * p.s_i1 + i20 * p.s_i2 + j10 * p.s_j1 + j20 * p.s_j2;
-    double* dp = dst + doff + i10 * p.d_i1 + i20 * p.d_i2 + j10 * p.d_j1 + j20 * p.d_j2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pitch = p.pitch;
-    {
-        const long long lane_s = lane * p.s_i1, step_s = 32 * p.s_i1;
-        int j1 = warp % tj1, j2 = warp / tj1;
-        const int dj1 = 8 % tj1, dj2 = 8 / tj1;
-        for (int r0 = warp; r0 < cj; r0 += 8 * U) {
-            double v[U][3];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = r0 + 8 * u;
-                if (r < cj) {
-                    const double* g = sp + j1 * p.s_j1 + j2 * p.s_j2 + lane_s;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        if (lane + 32 * k < ci) v[u][k] = g[k * step_s];
-                }
-                j1 += dj1; j2 += dj2;
-                if (j1 >= tj1) { j1 -= tj1; ++j2; }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int r = r0 + 8 * u;
-                if (r < cj) {
-                    double* t = tile + r * pitch + lane;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        if (lane + 32 * k < ci) t[32 * k] = v[u][k];
-                }
-            }
-        }
-    }
+    const TileGeom g = tile_geometry(src, dst, p, blockIdx.x);
+    tile_read_phase<U>(g, p, tile, threadIdx.x);      // permute_plan.cuh (host-checked)
     __syncthreads();
-    {
-        const long long lane_d = lane * p.d_j1, step_d = 32 * p.d_j1;
-        int i1 = warp % ti1, i2 = warp / ti1;
-        const int di1 = 8 % ti1, di2 = 8 / ti1;
-        for (int r = warp; r < ci; r += 8) {
-            double* g = dp + i1 * p.d_i1 + i2 * p.d_i2 + lane_d;
-            const double* t = tile + lane * pitch + r;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (lane + 32 * k < cj) g[k * step_d] = t[32 * k * pitch];
-            i1 += di1; i2 += di2;
-            if (i1 >= ti1) { i1 -= ti1; ++i2; }
-        }
-    }
+    tile_write_phase(g, p, tile, threadIdx.x);
 }
 
 // same fastest index on both sides: one thread per element, inner index fastest.  T = double2
@@ -259,51 +174,17 @@ __global__ void __launch_bounds__(256) copy_flat_kernel(const double* __restrict
 void strided_copy(Context* ctx, const double* src, double* dst, int rank, const long long* dims,
                   const long long* sstride, const long long* dstride) {
     TNR_CHECK(rank >= 0 && rank <= 16, "strided_copy: rank out of range");
-    struct D { long long n, s, d; };
-    std::vector<D> v;
-    long long total = 1;
-    for (int i = 0; i < rank; ++i) {
-        TNR_CHECK(dims[i] >= 0, "strided_copy: negative dim");
-        total *= dims[i];
-        if (dims[i] != 1) v.push_back({dims[i], sstride[i], dstride[i]});
-    }
+    CopyPlan plan = plan_strided_copy(rank, dims, sstride, dstride, ctx->permute_tile);
+    TNR_CHECK(plan.error == nullptr, plan.error ? plan.error : "");
+    const long long total = plan.total;
     if (total == 0) return;
-    // order by destination stride, then merge groups that are adjacent on both sides
-    std::stable_sort(v.begin(), v.end(), [](const D& a, const D& b) { return a.d < b.d; });
-    std::vector<D> m;
-    for (auto& x : v) {
-        if (!m.empty() && m.back().s * m.back().n == x.s && m.back().d * m.back().n == x.d)
-            m.back().n *= x.n;
-        else
-            m.push_back(x);
-    }
     ctx->ctr.permute_bytes += 16.0 * (double)total;
-    if (m.empty()) {  // single element
-        m.push_back({1, 1, 1});
-    }
-    if (m.size() == 1 && m[0].s == 1 && m[0].d == 1) {
+    CopyParams& p = plan.p;
+    if (plan.kind == COPY_FLAT) {
         int vec = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
         long long work = vec ? (total + 1) / 2 : total;
         copy_flat_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(src, dst, total, vec);
-        TNR_CUDA(cudaGetLastError());
-        ctx->ctr.launches++;
-        return;
-    }
-    TNR_CHECK((int)m.size() <= MAXR + 3, "strided_copy: too many index groups after merging");
-    // dst-fastest is m[0]; find src-fastest
-    size_t js = 0;
-    for (size_t i = 1; i < m.size(); ++i)
-        if (m[i].s < m[js].s) js = i;
-    CopyParams p{};
-    if (js == 0) {
-        TNR_CHECK((int)m.size() - 1 <= MAXR, "strided_copy: too many index groups after merging");
-        p.ni = m[0].n; p.si_s = m[0].s; p.si_d = m[0].d;
-        p.rank = 0;
-        for (size_t i = 1; i < m.size(); ++i) {
-            p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
-            p.rank++;
-        }
-        p.total = total;
+    } else if (plan.kind == COPY_ROWS) {
         bool vec = ctx->permute_unroll > 1 && p.si_s == 1 && p.si_d == 1 && p.ni % 2 == 0 &&
                    (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
         for (int d = 0; vec && d < p.rank; ++d) vec = p.ss[d] % 2 == 0 && p.ds[d] % 2 == 0;
@@ -316,47 +197,8 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
             copy_rows_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, p);
         }
     } else {
-        // i1 = source-fastest group, j1 = destination-fastest group (m[0]); i2 / j2 = the
-        // groups that continue them contiguously in the source / destination, if any
-        const size_t none = (size_t)-1;
-        size_t i2 = none, j2 = none;
-        for (size_t i = 1; i < m.size(); ++i)
-            if (i != js && m[i].s == m[js].s * m[js].n) i2 = i;
-        for (size_t i = 1; i < m.size(); ++i)
-            if (i != js && i != i2 && m[i].d == m[0].d * m[0].n) j2 = i;
-        const int TGT = ctx->permute_tile;  // composite run length (doubles): 96, opt-in 32 | 48 | 64
-        auto split = [&](long long n1, long long n2, int& T1, int& T2) {
-            if (n1 >= TGT) { T1 = TGT; T2 = 1; }
-            else if (n1 > 48 || n2 <= 1) { T1 = (int)std::min<long long>(n1, 48); T2 = 1;
-                                           if (n1 <= TGT) T1 = (int)n1; }
-            else { T1 = (int)n1; T2 = (int)std::max<long long>(1, std::min<long long>(n2, TGT / n1)); }
-        };
-        p.n_i1 = m[js].n; p.s_i1 = m[js].s; p.d_i1 = m[js].d;
-        p.n_j1 = m[0].n;  p.s_j1 = m[0].s;  p.d_j1 = m[0].d;
-        p.n_i2 = (i2 != none) ? m[i2].n : 1; p.s_i2 = (i2 != none) ? m[i2].s : 0;
-        p.d_i2 = (i2 != none) ? m[i2].d : 0;
-        p.n_j2 = (j2 != none) ? m[j2].n : 1; p.s_j2 = (j2 != none) ? m[j2].s : 0;
-        p.d_j2 = (j2 != none) ? m[j2].d : 0;
-        split(p.n_i1, p.n_i2, p.TI1, p.TI2);
-        split(p.n_j1, p.n_j2, p.TJ1, p.TJ2);
-        p.tiles_i1 = (p.n_i1 + p.TI1 - 1) / p.TI1;
-        p.tiles_i2 = (p.n_i2 + p.TI2 - 1) / p.TI2;
-        p.tiles_j1 = (p.n_j1 + p.TJ1 - 1) / p.TJ1;
-        p.tiles_j2 = (p.n_j2 + p.TJ2 - 1) / p.TJ2;
-        p.pitch = p.TI1 * p.TI2 + 1;
-        if ((p.pitch & 1) == 0) p.pitch += 1;
-        p.rank = 0;
-        long long outer = 1;
-        for (size_t i = 1; i < m.size(); ++i) {
-            if (i == js || i == i2 || i == j2) continue;
-            TNR_CHECK(p.rank < MAXR, "strided_copy: too many index groups after merging");
-            p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
-            p.rank++;
-            outer *= m[i].n;
-        }
-        long long blocks = p.tiles_i1 * p.tiles_i2 * p.tiles_j1 * p.tiles_j2 * outer;
-        TNR_CHECK(blocks < (1LL << 31), "strided_copy: grid too large");
-        size_t smem = (size_t)p.TJ1 * p.TJ2 * p.pitch * sizeof(double);
+        const long long blocks = plan.blocks;
+        const size_t smem = plan.smem;
         static bool configured = false;
         if (!configured) {
             TNR_CUDA(cudaFuncSetAttribute(copy_tiled_kernel,
