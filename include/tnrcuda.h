@@ -53,7 +53,10 @@ int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
 int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
 /* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests);
  * "disable_subspace", "disable_block_jacobi", "disable_precondition" switch the fast SVD/eigh
- * paths off; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes */
+ * paths off; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes;
+ * "ozaki_crt" = N (0 = off, default; 14..18) selects its CRT variant with N moduli instead;
+ * "permute_unroll" = 1 (default) | 2 | 4 and "permute_tile" = 32 | 48 | 64 | 96 (default) select
+ * variants of the permute kernels.  Unknown keys and out-of-range values are errors. */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
  * library stream; read returns the summed milliseconds, flops and the launch count. */
