@@ -64,3 +64,24 @@ def test_chi24_rotation_plan(shim):
     kind, got, info = _run(shim, a, (5, 3, 1, 2, 0, 4), 4, 96)
     assert np.array_equal(got, np.transpose(a, (5, 3, 1, 2, 0, 4)))
     assert kind == 3
+
+
+def test_planner_fuzz_random_permutations(shim):
+    """300 random shapes / permutations (ranks 1..6, legs 1..9 with an occasional long leg) through
+    the default plan (tile 96) and the opt-in variants."""
+    rng = np.random.default_rng(2024)
+    kinds = set()
+    for case in range(300):
+        rank = int(rng.integers(1, 7))
+        dims = [int(rng.integers(1, 10)) for _ in range(rank)]
+        if rng.random() < 0.3:
+            dims[int(rng.integers(0, rank))] = int(rng.integers(30, 130))
+        while np.prod(dims) > 400000:
+            dims[int(np.argmax(dims))] //= 2
+        perm = [int(x) for x in rng.permutation(rank)]
+        a = rng.standard_normal(dims)
+        unroll, tile = [(1, 96), (4, 96), (2, 64), (4, 48)][case % 4]
+        kind, got, _ = _run(shim, a, perm, unroll, tile)
+        kinds.add(kind)
+        assert np.array_equal(got, np.transpose(a, perm)), (dims, perm, unroll, tile)
+    assert kinds == {1, 2, 3}
