@@ -9,24 +9,10 @@
 
 using namespace tnr;
 
-extern "C" {
-// TensorKit-style permute: new leg k = old leg perm[k]; column-major data.
-// Returns the plan kind (1 flat, 2 rows, 3 tiled) or a negative number on error;
-// info[0..5] = TI1*TI2, TJ1*TJ2, blocks, smem bytes, pitch, merged outer rank.
-int permute_host(const double* src, double* dst, int rank, const long long* dims, const int* perm,
-                 int unroll, int tile, long long* info) {
-    long long sst[16], dims_out[16], dst_st[16], src_st_for_out[16];
-    long long s = 1;
-    for (int i = 0; i < rank; ++i) { sst[i] = s; s *= dims[i]; }
-    long long d = 1;
-    for (int k = 0; k < rank; ++k) {
-        int q = perm[k];
-        dims_out[k] = dims[q];
-        dst_st[k] = d;
-        d *= dims[q];
-        src_st_for_out[k] = sst[q];
-    }
-    CopyPlan plan = plan_strided_copy(rank, dims_out, src_st_for_out, dst_st, tile);
+static int run_plan(const double* src, double* dst, int rank, const long long* dims,
+                    const long long* sst, const long long* dst_st, int unroll, int tile,
+                    long long* info) {
+    CopyPlan plan = plan_strided_copy(rank, dims, sst, dst_st, tile);
     if (plan.error) return -1;
     const CopyParams& p = plan.p;
     info[0] = (long long)p.TI1 * p.TI2; info[1] = (long long)p.TJ1 * p.TJ2;
@@ -63,5 +49,31 @@ int permute_host(const double* src, double* dst, int rank, const long long* dims
         }
     }
     return (int)plan.kind;
+}
+
+extern "C" {
+// TensorKit-style permute: new leg k = old leg perm[k]; column-major data.
+// Returns the plan kind (1 flat, 2 rows, 3 tiled) or a negative number on error;
+// info[0..5] = TI1*TI2, TJ1*TJ2, blocks, smem bytes, pitch, merged outer rank.
+int permute_host(const double* src, double* dst, int rank, const long long* dims, const int* perm,
+                 int unroll, int tile, long long* info) {
+    long long sst[16], dims_out[16], dst_st[16], src_st_for_out[16];
+    long long s = 1;
+    for (int i = 0; i < rank; ++i) { sst[i] = s; s *= dims[i]; }
+    long long d = 1;
+    for (int k = 0; k < rank; ++k) {
+        int q = perm[k];
+        dims_out[k] = dims[q];
+        dst_st[k] = d;
+        d *= dims[q];
+        src_st_for_out[k] = sst[q];
+    }
+    return run_plan(src, dst, rank, dims_out, src_st_for_out, dst_st, unroll, tile, info);
+}
+// tnr_strided_copy: dst[sum i_k dstride_k] = src[sum i_k sstride_k] (element strides)
+int strided_copy_host(const double* src, double* dst, int rank, const long long* dims,
+                      const long long* sstride, const long long* dstride, int unroll, int tile,
+                      long long* info) {
+    return run_plan(src, dst, rank, dims, sstride, dstride, unroll, tile, info);
 }
 }

@@ -85,3 +85,45 @@ def test_planner_fuzz_random_permutations(shim):
         kinds.add(kind)
         assert np.array_equal(got, np.transpose(a, perm)), (dims, perm, unroll, tile)
     assert kinds == {1, 2, 3}
+
+
+def test_strided_copy_sub_blocks_fuzz(shim):
+    """`tnr_strided_copy` as the block-sparse layer uses it (symmetric.py: matricize, sym_slice,
+    sym_scatter): a permuted sub-block of a larger source array into a sub-block of a larger
+    destination array, both with non-compact strides."""
+    rng = np.random.default_rng(7)
+    for case in range(200):
+        rank = int(rng.integers(1, 6))
+        big_s = [int(rng.integers(2, 12)) for _ in range(rank)]
+        big_d_perm = [int(x) for x in rng.permutation(rank)]
+        dims = [int(rng.integers(1, b + 1)) for b in big_s]
+        off_s = [int(rng.integers(0, b - d + 1)) for b, d in zip(big_s, dims)]
+        # destination: the same legs in permuted order inside a larger array
+        big_d = [dims[q] + int(rng.integers(0, 4)) for q in big_d_perm]
+        off_d = [int(rng.integers(0, b - dims[q] + 1)) for b, q in zip(big_d, big_d_perm)]
+        src = rng.standard_normal(big_s)
+        dst = np.full(big_d, np.nan)
+        want = dst.copy()
+        sl_s = tuple(slice(o, o + d) for o, d in zip(off_s, dims))
+        sl_d = tuple(slice(o, o + dims[q]) for o, q in zip(off_d, big_d_perm))
+        want[sl_d] = np.transpose(src[sl_s], big_d_perm)
+        # column-major element strides
+        fs = np.ascontiguousarray(np.transpose(src).reshape(-1))
+        fd = np.ascontiguousarray(np.transpose(dst).reshape(-1))
+        st_s = np.cumprod([1] + big_s[:-1]).tolist()
+        st_d_pos = np.cumprod([1] + big_d[:-1]).tolist()
+        st_d = [0] * rank
+        for pos, q in enumerate(big_d_perm):
+            st_d[q] = st_d_pos[pos]
+        base_s = sum(o * s for o, s in zip(off_s, st_s))
+        base_d = sum(o * s for o, s in zip(off_d, st_d_pos))
+        info = (C.c_longlong * 6)()
+        unroll, tile = [(1, 96), (4, 96), (2, 48)][case % 3]
+        kind = shim.strided_copy_host(
+            C.c_void_p(fs.ctypes.data + 8 * base_s), C.c_void_p(fd.ctypes.data + 8 * base_d), rank,
+            (C.c_longlong * rank)(*dims), (C.c_longlong * rank)(*st_s), (C.c_longlong * rank)(*st_d),
+            unroll, tile, info)
+        assert kind in (1, 2, 3)
+        got = np.transpose(fd.reshape(tuple(reversed(big_d))))
+        assert np.array_equal(np.isnan(got), np.isnan(want)), (big_s, dims, big_d_perm)
+        assert np.array_equal(got[sl_d], want[sl_d]), (big_s, dims, big_d_perm)
