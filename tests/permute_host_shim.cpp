@@ -21,7 +21,26 @@ static int run_plan(const double* src, double* dst, int rank, const long long* d
     if (plan.kind == COPY_FLAT) {
         std::memcpy(dst, src, sizeof(double) * (size_t)plan.total);
     } else if (plan.kind == COPY_ROWS) {
-        // the arithmetic of copy_rows_kernel, one "thread" per element
+        CopyParams q = p;
+        const bool vec = unroll > 1 && rows_vectorize(q, (uintptr_t)src, (uintptr_t)dst);
+        if (vec) info[5] = -1;   // tells the test that the 16-byte path ran
+        // the arithmetic of copy_rows_kernel<T>, one "thread" per element of T
+        struct D2 { double x, y; };
+        if (vec) {
+            const D2* s2 = reinterpret_cast<const D2*>(src);
+            D2* d2 = reinterpret_cast<D2*>(dst);
+            for (long long idx = 0; idx < q.total; ++idx) {
+                long long i = idx % q.ni, rest = idx / q.ni;
+                long long soff = i * q.si_s, doff = i * q.si_d;
+                for (int dd = 0; dd < q.rank; ++dd) {
+                    long long k = rest % q.dims[dd];
+                    rest /= q.dims[dd];
+                    soff += k * q.ss[dd];
+                    doff += k * q.ds[dd];
+                }
+                d2[doff] = s2[soff];
+            }
+        } else
         for (long long idx = 0; idx < p.total; ++idx) {
             long long i = idx % p.ni, rest = idx / p.ni;
             long long soff = i * p.si_s, doff = i * p.si_d;

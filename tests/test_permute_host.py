@@ -127,3 +127,23 @@ def test_strided_copy_sub_blocks_fuzz(shim):
         got = np.transpose(fd.reshape(tuple(reversed(big_d))))
         assert np.array_equal(np.isnan(got), np.isnan(want)), (big_s, dims, big_d_perm)
         assert np.array_equal(got[sl_d], want[sl_d]), (big_s, dims, big_d_perm)
+
+
+def test_rows_16_byte_path_on_host(shim):
+    """The equal-fastest-leg copy on double2 elements (`rows_vectorize`): taken for even shared
+    runs with even outer strides, declined otherwise; same result either way."""
+    rng = np.random.default_rng(3)
+    took = 0
+    for dims, perm in [((24, 6, 5, 4), (0, 3, 2, 1)), ((24, 24, 24, 24), (0, 3, 1, 2)),
+                       ((8, 3, 5), (0, 2, 1)), ((7, 4, 6), (0, 2, 1)), ((12,) * 6, (0, 5, 4, 3, 1, 2)),
+                       ((2, 9, 9), (0, 2, 1))]:
+        a = rng.standard_normal(dims)
+        for unroll in (1, 4):
+            kind, got, info = _run(shim, a, perm, unroll, 96)
+            assert kind == 2 and np.array_equal(got, np.transpose(a, perm))
+            if unroll == 4 and info[5] == -1:
+                took += 1
+                assert dims[0] % 2 == 0
+            if dims[0] % 2 == 1:
+                assert info[5] != -1
+    assert took >= 4

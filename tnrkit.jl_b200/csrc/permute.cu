@@ -185,12 +185,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         long long work = vec ? (total + 1) / 2 : total;
         copy_flat_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(src, dst, total, vec);
     } else if (plan.kind == COPY_ROWS) {
-        bool vec = ctx->permute_unroll > 1 && p.si_s == 1 && p.si_d == 1 && p.ni % 2 == 0 &&
-                   (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
-        for (int d = 0; vec && d < p.rank; ++d) vec = p.ss[d] % 2 == 0 && p.ds[d] % 2 == 0;
-        if (vec) {
-            p.ni /= 2; p.total /= 2;
-            for (int d = 0; d < p.rank; ++d) { p.ss[d] /= 2; p.ds[d] /= 2; }
+        if (ctx->permute_unroll > 1 && rows_vectorize(p, (uintptr_t)src, (uintptr_t)dst)) {
             copy_rows_kernel<double2><<<(unsigned)((p.total + 255) / 256), 256, 0, ctx->stream>>>(
                 reinterpret_cast<const double2*>(src), reinterpret_cast<double2*>(dst), p);
         } else {

@@ -152,6 +152,19 @@ inline CopyPlan plan_strided_copy(int rank, const long long* dims, const long lo
     return out;
 }
 
+// Row copy on 16-byte elements: possible when the shared fastest run is contiguous and even on
+// both sides, every other stride is even and both base addresses are 16-byte aligned.  Rewrites
+// the parameters in units of double2 and returns true, or leaves them untouched.
+inline bool rows_vectorize(CopyParams& p, uintptr_t src_addr, uintptr_t dst_addr) {
+    bool vec = p.si_s == 1 && p.si_d == 1 && p.ni % 2 == 0 && src_addr % 16 == 0 &&
+               dst_addr % 16 == 0;
+    for (int d = 0; vec && d < p.rank; ++d) vec = p.ss[d] % 2 == 0 && p.ds[d] % 2 == 0;
+    if (!vec) return false;
+    p.ni /= 2; p.total /= 2;
+    for (int d = 0; d < p.rank; ++d) { p.ss[d] /= 2; p.ds[d] /= 2; }
+    return true;
+}
+
 // ---- per-thread phases of the tiled kernel with U rows of loads in flight -------------------
 struct TileGeom {
     const double* sp;
