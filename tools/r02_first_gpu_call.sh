@@ -31,6 +31,9 @@ step ozaki_crt_check 600 python tools/ozaki_crt_check.py
 # 3. permute variants (decides the default of permute_unroll / permute_tile)
 step permute_perf_24 300 python tools/permute_perf.py 24
 step permute_perf_16 120 python tools/permute_perf.py 16
+# 3b. ncu evidence for the permute variants (durations and DRAM bytes per launch; not bench values)
+step permute_ncu 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+  --clock-control none -k regex:copy_ -c 120 --csv --log-file "$OUT/permute_ncu.csv" python tools/permute_perf.py 24
 # 4. configs[3] groundwork: ATRG_3D dense vs factored at chi=24, factored at chi=48
 step atrg3d24_dense 300 python tools/atrg3d_bench.py --chi 24 --steps 4 --dense
 step atrg3d24_factored 600 python tools/atrg3d_bench.py --chi 24 --steps 4 --phases
