@@ -1,6 +1,6 @@
 """CPU tests of the factored ATRG_3D step (tnrkit.jl_b200/atrg3d_factored.py): the host layer only
 sequences C-ABI primitives, which tests/abi_emulator.py executes with numpy here (tests only; the
-`-m gpu` twin tests/test_gpu_zzz_atrg3d_factored.py runs the same sequences on the device).
+`-m gpu` twin tests/test_gpu_atrg3d_factored.py runs the same sequences on the device).
 
 What is checked: the two-factor algebra (leg names, implicit products, trace), the truncated SVD
 of an implicit operator against a dense LAPACK SVD, the whole step against the oracle's

@@ -1,9 +1,7 @@
 """Device twin of tests/test_atrg3d_factored_emulated.py: the factored ATRG_3D step
 (tnrkit.jl_b200/atrg3d_factored.py) through the real C ABI -- `tnr_orth_r`, the implicit products,
 the subspace-iteration SVD, chunked TSQR -- against the oracle, against the dense device step
-(`tnr_atrg3d_step`) and, on a box with 2 GPUs, sharded over NCCL.
-
-(File name: sorted after the other `-m gpu` files so that they run first under `-x`.)"""
+(`tnr_atrg3d_step`) and, on a box with 2 GPUs, sharded over NCCL."""
 import os
 import socket
 import sys

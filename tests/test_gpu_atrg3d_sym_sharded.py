@@ -2,9 +2,7 @@
 _atrg3d_tail_sharded; reference body: src/schemes/atrg3d.jl:34-83 on the Z2 tensor of
 test/schemes.jl:8).  CPU twins on the emulated primitives:
 tests/test_host_sequencing_emulated.py::test_emulated_atrg3d_chunked_tail_matches_oracle and
-tests/test_multiproc_gloo.py::test_block_sparse_atrg3d_sharded_world2.
-
-(File name: written after the round's GPU budget was spent, so it sorts last under `-x`.)"""
+tests/test_multiproc_gloo.py::test_block_sparse_atrg3d_sharded_world2."""
 import os
 import socket
 import sys
@@ -18,14 +16,19 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("chi,n,chunk", [(4, 3, 1), (6, 2, 2), (8, 3, 3)])
+# chi = 8 is NOT a parity case: truncrank(8) cuts a degenerate multiplet of the 3D Ising ATRG
+# spectrum and the oracle's own norms move by 8e-3 under a 1e-14 perturbation (round 1's red test);
+# chi = 4, 6, 10 move by <= 2e-13.  tests/conditioning.py refuses ill-conditioned cases.
+@pytest.mark.parametrize("chi,n,chunk", [(4, 3, 1), (6, 2, 2), (10, 3, 3)])
 def test_block_sparse_atrg3d_chunked_tail_on_device(tk, chi, n, chunk):
+    from conditioning import require_well_conditioned
     from tnrkit.jl_b200 import symmetric
 
     T = tk.classical_ising_3D()
+    ref = require_well_conditioned(lambda t: o.run(o.ATRG_3D(t), chi, n), np.asarray(T),
+                                   f"ATRG_3D chi={chi} n={n}")
     s = tk.ATRG_3D(T, symmetric=True, sym_chunk=chunk)
     got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
-    ref = np.array(o.run(o.ATRG_3D(np.asarray(T)), chi, n))
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-10
     plan = symmetric.LAST_PLAN["atrg3d"]
     assert plan["world"] == 1 and plan["chunks_AX"] >= 2 and plan["chunks_YD"] >= 2
@@ -81,7 +84,10 @@ def test_block_sparse_atrg3d_sharded_two_gpus():
         assert p.exitcode == 0
     import tnrkit.jl_b200 as tk
 
-    ref = np.array(o.run(o.ATRG_3D(np.asarray(tk.classical_ising_3D())), chi, n))
+    from conditioning import require_well_conditioned
+
+    ref = require_well_conditioned(lambda t: o.run(o.ATRG_3D(t), chi, n),
+                                   np.asarray(tk.classical_ising_3D()), f"ATRG_3D chi={chi} n={n}")
     for r in range(2):
         got, plan = res[r]
         assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, r

@@ -4,9 +4,7 @@ HOTRG / ATRG at their sizes and tolerances (test/schemes.jl:18-164, on the Z2 te
 `T = classical_ising()` as there, and on the dense `Trivial` tensor), and the oracle's restatement
 evaluated on the very state the device run produced.  CPU twins:
 tests/test_host_sequencing_emulated.py::test_emulated_cft_observables_*,
-tests/test_oracle_golden.py::test_oracle_cft_data_reference_testsets.
-
-(File name: written after the round's GPU budget was spent, so it sorts last under `-x`.)"""
+tests/test_oracle_golden.py::test_oracle_cft_data_reference_testsets."""
 import numpy as np
 import pytest
 

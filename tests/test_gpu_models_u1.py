@@ -2,9 +2,7 @@
 truncrank(16), maxiter(25), rtol 1e-3) through the product path on the GPU -- clock (Trivial, ZN),
 six-vertex (Trivial, U1), real phi^4 (Trivial, Z2) -- and the block-sparse steps on U(1) / Z3 /
 Z2 sectors against the oracle.  Device twin of the `u1` / `models` tests in
-tests/test_host_sequencing_emulated.py and of tests/test_oracle_golden.py::test_models_golden_*.
-
-(File name: sorted after the other `-m gpu` files so that they run first under `-x`.)"""
+tests/test_host_sequencing_emulated.py and of tests/test_oracle_golden.py::test_models_golden_*."""
 import math
 
 import numpy as np

@@ -2,9 +2,7 @@
 ozaki_crt_split_kernel, ozaki_tile_kernel<true>, ozaki_crt_reconstruct_kernel in
 csrc/gemm_ozaki.cu; scalar arithmetic in csrc/crt_math.cuh, host-checked by
 tests/test_crt_math_host.py): accuracy against extended precision and against the bit-level model
-(oracle/ozaki_model.py: multiply_crt), and a HOTRG_3D run with the engine on.
-
-(File name: written after the round's GPU budget was spent, so it sorts last under `-x`.)"""
+(oracle/ozaki_model.py: multiply_crt), and a HOTRG_3D run with the engine on."""
 import ctypes as C
 
 import numpy as np

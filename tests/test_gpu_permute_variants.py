@@ -2,9 +2,7 @@
 "permute_unroll"` = 2 | 4, `"permute_tile"` = 32 | 48 | 64: copy_tiled_mlp_kernel<U>, copy_rows_kernel<double2>, csrc/permute.cu)
 against numpy and against the default kernels -- pure data movement, bit exact.  Covers ragged
 tiles (extents that are no multiple of the 96-element composite run), odd extents (no 16-byte
-path), the equal-fastest-leg case and the chi = 24 rotation of hotrg3d.jl:134.
-
-(File name: written after the round's GPU budget was spent, so it sorts last under `-x`.)"""
+path), the equal-fastest-leg case and the chi = 24 rotation of hotrg3d.jl:134."""
 import numpy as np
 import pytest
 

@@ -245,7 +245,7 @@ def test_emulated_spaces_testset(tk, emu, name, model):
     """test/spaces.jl:5-24: every 2D scheme takes every kind of space through 25 steps at the odd
     truncrank(7) without a space mismatch (here: the Z2 Ising and the U(1) six-vertex tensor on
     the block-sparse path; `classical_ising(Trivial)` runs on the dense device path, GPU twin in
-    tests/test_gpu_zz_models_u1.py; the Gross-Neveu tensor is fermionic: out of scope).  On top
+    tests/test_gpu_models_u1.py; the Gross-Neveu tensor is fermionic: out of scope).  On top
     of the reference's `isa(..., Any)`: all 26 norms are finite and positive, every block obeys
     the conservation law, and contracted bonds keep opposite arrows."""
     T = tk.classical_ising() if model == "ising_z2" else tk.sixvertex(tk.U1Irrep)

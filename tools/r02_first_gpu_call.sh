@@ -17,16 +17,16 @@ step() {  # step <name> <timeout-seconds> <command...>
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/gpu.txt" 2>&1
 # 1. the suite that was green in round 1 (regression check after the host-layer changes)
 step tests_round1 900 python -m pytest tests -q -m gpu -x --durations=15 \
-  --ignore=tests/test_gpu_zz_models_u1.py --ignore=tests/test_gpu_zzz_atrg3d_factored.py \
-  --ignore=tests/test_gpu_zzzz_atrg3d_sym_sharded.py --ignore=tests/test_gpu_zzzz_cft_observables.py \
-  --ignore=tests/test_gpu_zzzzz_permute_unroll.py --ignore=tests/test_gpu_zzzzzz_ozaki_crt.py
+  --ignore=tests/test_gpu_models_u1.py --ignore=tests/test_gpu_atrg3d_factored.py \
+  --ignore=tests/test_gpu_atrg3d_sym_sharded.py --ignore=tests/test_gpu_cft_observables.py \
+  --ignore=tests/test_gpu_permute_variants.py --ignore=tests/test_gpu_ozaki_crt.py
 # 2. device twins that have never run (no -x: collect every failure in one call)
-step tests_models_u1 600 python -m pytest tests/test_gpu_zz_models_u1.py -q -m gpu --durations=10
-step tests_atrg3d_factored 900 python -m pytest tests/test_gpu_zzz_atrg3d_factored.py -q -m gpu --durations=10
-step tests_atrg3d_sym_sharded 300 python -m pytest tests/test_gpu_zzzz_atrg3d_sym_sharded.py -q -m gpu
-step tests_cft 600 python -m pytest tests/test_gpu_zzzz_cft_observables.py -q -m gpu --durations=10
-step tests_permute_unroll 300 python -m pytest tests/test_gpu_zzzzz_permute_unroll.py -q -m gpu
-step tests_ozaki_crt 600 python -m pytest tests/test_gpu_zzzzzz_ozaki_crt.py -q -m gpu
+step tests_models_u1 600 python -m pytest tests/test_gpu_models_u1.py -q -m gpu --durations=10
+step tests_atrg3d_factored 900 python -m pytest tests/test_gpu_atrg3d_factored.py -q -m gpu --durations=10
+step tests_atrg3d_sym_sharded 300 python -m pytest tests/test_gpu_atrg3d_sym_sharded.py -q -m gpu
+step tests_cft 600 python -m pytest tests/test_gpu_cft_observables.py -q -m gpu --durations=10
+step tests_permute_unroll 300 python -m pytest tests/test_gpu_permute_variants.py -q -m gpu
+step tests_ozaki_crt 600 python -m pytest tests/test_gpu_ozaki_crt.py -q -m gpu
 step ozaki_crt_check 600 python tools/ozaki_crt_check.py
 # 3. permute variants (decides the default of permute_unroll / permute_tile)
 step permute_perf_24 300 python tools/permute_perf.py 24
