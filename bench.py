@@ -18,6 +18,14 @@ z-compression; the JSON line says which.
 
 Timing: CUDA events on the engine stream, barrier + synchronize on both sides, max over
 ranks.  Inputs (1.5 GB at chi=24) exceed the 126 MB L2, so no explicit flush is needed.
+
+Time box.  One steady-state chi=24 step is 9.15e15 FP64 flop, i.e. >= 229 s at the nominal
+40 TFLOP/s of the chip, so `--steps 20 --warmup 5` cannot fit any driver limit at N=1.  The run
+therefore has a wall budget (`--time-budget`, default 780 s counted from interpreter start;
+0 disables it): warm-up stops as soon as >= 3 iterations ran AND every leg equals chi (RG
+iteration 3) when the requested count would overrun; timed steps run until the next one would
+overrun, never fewer than min(2, K).  The JSON line reports the steps and warm-ups actually
+done (`steps`, `warmup`) and what was asked for (`steps_requested`, `warmup_requested`).
 """
 from __future__ import annotations
 
@@ -30,8 +38,13 @@ import sys
 import threading
 import time
 
+T_START = time.time()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+NOMINAL_FP64_TFLOPS = 40.0      # B200 FP64 tensor peak (vendor figure; no measured FP64 entry in
+#                                 MEASURED_PEAKS.json and none in the profiling guide)
+DMMA_FMA_PER_CLK_SM = 64        # DMMA.8x8x4 pipe: 64 FP64 FMA / clk / SM (148 SMs)
 
 METRIC = "HOTRG_3D Ising chi=%d s/RG-step"
 
@@ -130,12 +143,54 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # CPU arms (oracle port; the reference itself is Julia and cannot run in this image)
 # ----------------------------------------------------------------------------------
-def cpu_sample(chi: int, target_s: float = 12.0):
-    """Times the oracle's dominant contraction of the same workload on the host cores.
+_ORACLE_STEP_CACHE = {}
 
-    Sample: R[(a y1' y1), cols] = Qk^T Pk[:, cols] with K = M = chi^3, i.e. a column block of
-    ONE of the 3*chi^2 (f,d) chunk contractions of an RG step, sized by a calibration run to
-    about `target_s` seconds; scaled to the full step by flops."""
+
+def _host_threads():
+    try:
+        import threadpoolctl
+        return max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_full_step_seconds(chi_s: int):
+    """Times ONE REAL steady-state `step!` + `finalize!` of the oracle's HOTRG_3D (projector
+    Gram contractions, eigh, the chi^11 contraction, permutes) at a bond dimension the host can
+    hold (chi_s^8 doubles), on the 3D Ising tensor after the iterations that saturate the legs."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tnr_oracle as o
+
+    if chi_s not in _ORACLE_STEP_CACHE:
+        sch = o.HOTRG_3D(o.classical_ising_3D())
+        sch.finalize()
+        while not all(d == chi_s for d in sch.T.shape):
+            sch.step(chi_s)
+            sch.finalize()
+        _ORACLE_STEP_CACHE[chi_s] = sch.T.copy()
+    if ("t", chi_s) not in _ORACLE_STEP_CACHE:      # timed once per process
+        sch = o.HOTRG_3D(_ORACLE_STEP_CACHE[chi_s])
+        t0 = time.perf_counter()
+        sch.step(chi_s)
+        n = sch.finalize()
+        _ORACLE_STEP_CACHE[("t", chi_s)] = time.perf_counter() - t0
+        assert np.isfinite(n)
+    return _ORACLE_STEP_CACHE[("t", chi_s)]
+
+
+def cpu_sample(chi: int, target_s: float = 10.0, chi_small: int = 10):
+    """Bounded CPU sample of the workload on the host cores (oracle port, numpy + LAPACK/BLAS).
+
+    (1) the oracle's dominant contraction at the FULL size: R[(a y1' y1), cols] = Qk^T Pk[:, cols]
+        with K = M = chi^3 -- a column block of ONE of the 3*chi^2 (f,d) chunk contractions of
+        an RG step, sized by a calibration run to about `target_s` seconds.  s/RG-step =
+        step_flops(chi) / (dgemm flop rate of that sample): a LOWER bound of the CPU time (the
+        oracle's SVD / permute / memory-bound phases only add to it), i.e. the comparison
+        favours the CPU.
+    (2) validation of that flop model: one REAL full oracle step at chi_small (everything
+        included), compared with step_flops(chi_small) / the same flop rate."""
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -155,17 +210,24 @@ def cpu_sample(chi: int, target_s: float = 12.0):
     R = o.hotrg3d_chunk_contract(Qk, Pk)
     dt = time.perf_counter() - t0
     assert R.shape == (m, ncols)
+    del Qk, Pk, R
     flops = 2.0 * m * m * ncols
-    sec_per_step = dt * step_flops(chi) / flops
-    try:
-        import threadpoolctl
-        cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
-    except Exception:
-        cores = os.cpu_count() or 1
+    rate = flops / dt
+    sec_per_step = step_flops(chi) / rate
+    cores = _host_threads()
     sample = (f"{ncols} of {m} columns of one of the {3 * chi * chi} (f,d) chunk contractions "
-              f"(K=M={m}) per RG step, numpy/BLAS dgemm, {dt:.1f}s, {flops / dt / 1e9:.0f} GF/s; "
-              f"scaled by flops to the full step")
-    return sec_per_step, cores, sample
+              f"(K=M={m}) per RG step, numpy/BLAS dgemm, {dt:.1f}s, {rate / 1e9:.0f} GF/s; "
+              f"scaled by flops to the full step (lower bound: SVD/permute phases not added)")
+    validation = None
+    if chi_small and chi_small < chi:
+        real = oracle_full_step_seconds(chi_small)
+        model = step_flops(chi_small) / rate
+        validation = {"chi": chi_small, "real_full_oracle_step_s": real,
+                      "flop_model_s": model, "real_over_model": real / model}
+        sample += (f"; flop model checked against one REAL full oracle step! + finalize! at "
+                   f"chi={chi_small}: {real:.2f}s measured vs {model:.2f}s modelled "
+                   f"(x{real / model:.2f})")
+    return sec_per_step, cores, sample, validation
 
 
 def run_reference(args):
@@ -173,20 +235,30 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
+    done = 0
+    cores = sample = validation = None
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_sample(args.chi, target_s=8.0)
+        # every step is a bounded sample (about 8 s of dgemm at the full size + one real oracle
+        # step at chi=10, timed once); the budget keeps the whole arm within a few minutes
+        if args.time_budget > 0 and i >= min(args.warmup + 2, args.warmup + args.steps) and \
+                time.time() - T_START > 0.4 * args.time_budget:
+            break
+        v, cores, sample, validation = cpu_sample(args.chi, target_s=6.0)
         if i >= args.warmup:
             vals.append(v)
-        log(f"reference sample {i}: {v:.0f} s/RG-step (extrapolated)")
+            done += 1
+        log(f"reference sample {i}: {v:.0f} s/RG-step (extrapolated by flops)")
     value = sum(vals) / len(vals)
     out = {
         "impl": "reference", "metric": METRIC % args.chi, "value": value, "unit": "s/RG-step",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "steps_requested": args.steps,
         "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"HOTRG_3D classical_ising_3D(Trivial) chi={args.chi}, "
                                "steady-state RG step (oracle port of the reference on host cores; "
-                               "the Julia reference cannot run in this image)"},
+                               "the Julia reference cannot run in this image)",
+                   "flop_model_validation": validation},
         "cpu_baseline": {"value": value, "unit": "s/RG-step", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "s/RG-step", "h2d_bytes_per_step": 0,
@@ -198,9 +270,8 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------
-def measure_fp64_peak(torch, dev):
-    """cuBLAS DGEMM 8192^3 burst (best of 5) -- the FP64 tensor-core denominator measured in
-    this run (MEASURED_PEAKS.json only holds HBM and bf16 numbers)."""
+def measure_fp64_dgemm(torch, dev):
+    """cuBLAS DGEMM 8192^3 burst (best of 5): context for the roofline, NOT its denominator."""
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=dev)
     b = torch.randn(n, n, dtype=torch.float64, device=dev)
@@ -239,7 +310,16 @@ def run_gpu(args):
     elif args.engine == "ozaki_crt":
         ctx.set_option("ozaki_crt", args.crt_moduli)
     chi = args.chi
-    peak = measure_fp64_peak(torch, dev) if rank == 0 else None
+    cublas = measure_fp64_dgemm(torch, dev) if rank == 0 else None
+    budget = float(args.time_budget)
+
+    def agree(*vals):
+        """max over ranks of a few host floats, so every rank takes the same decision."""
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
 
     scheme = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=world > 1)
     trunc = tk.truncrank(chi)
@@ -250,45 +330,76 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
+    def saturated():
+        return all(d == chi for d in scheme.T.dims)
+
+    # ---- warm-up: RG iterations 1..W (untimed) -------------------------------------------
+    w_done = 0
+    last = 0.0
+    while w_done < args.warmup:
+        if budget > 0 and w_done >= 3 and saturated():
+            elapsed, last_ = agree(time.time() - T_START, last)
+            if elapsed + (args.warmup - w_done + args.steps) * last_ > budget:
+                break
         t0 = time.perf_counter()
         scheme.step(trunc)
         norms.append(scheme.finalize())
         torch.cuda.synchronize()
+        last = time.perf_counter() - t0
+        w_done += 1
         if rank == 0:
-            log(f"warm-up step {w + 1}/{args.warmup}: dims {scheme.T.dims} norm {norms[-1]:.6e} "
-                f"{time.perf_counter() - t0:.1f}s")
-    if rank == 0 and not all(d == chi for d in scheme.T.dims):
+            log(f"warm-up step {w_done}/{args.warmup}: dims {scheme.T.dims} norm "
+                f"{norms[-1]:.6e} {last:.1f}s (t+{time.time() - T_START:.0f}s)")
+    if rank == 0 and not saturated():
         log(f"WARNING: bond dimensions not yet saturated after warm-up: {scheme.T.dims}")
 
+    # ---- timed steps: RG iterations W+1.. ------------------------------------------------
     nelem = scheme.T.size
-    pinned = torch.empty(nelem, dtype=torch.float64, pin_memory=True)
+    pinned = torch.empty(max(nelem, chi ** 6), dtype=torch.float64, pin_memory=True)
     sampler = ClockSampler(local)
     ctx.reset_counters()
     ctx.gemm_timing(True)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = []
     barrier()
     if rank == 0:
         sampler.start()
     wall0 = time.perf_counter()
     h2d = d2h = 0
+    est = 0.0
+    k_done = 0
+    min_steps = min(2, args.steps)
+    first_iter = w_done + 1
     for s in range(args.steps):
+        if budget > 0 and s >= min_steps:
+            elapsed, est_ = agree(time.time() - T_START, est)
+            if elapsed + 1.03 * est_ + 25.0 > budget:
+                if rank == 0:
+                    log(f"time budget: stopping after {s} timed steps (t+{elapsed:.0f}s, next "
+                        f"step ~{est_:.0f}s, budget {budget:.0f}s)")
+                break
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         # stage the step's input on the host (untimed), then time H2D + step + finalize
+        nelem = scheme.T.size
         pinned[:nelem].copy_(scheme.T.buf[:nelem])
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ev[s][0].record()
+        t0 = time.perf_counter()
+        e[0].record()
         scheme.T.buf[:nelem].copy_(pinned[:nelem], non_blocking=True)
-        ev[s][1].record()
+        e[1].record()
         scheme.step(trunc)
         norms.append(scheme.finalize())  # device->host read of the step's result (the norm)
-        ev[s][2].record()
+        e[2].record()
+        torch.cuda.synchronize()
+        est = max(est, time.perf_counter() - t0)
+        ev.append(e)
         h2d += nelem * 8
         d2h += 8
-        nelem = scheme.T.size
+        k_done += 1
         if rank == 0:
-            log(f"timed step {s + 1}/{args.steps}: norm {norms[-1]:.12e}")
+            log(f"timed step {k_done}/{args.steps}: norm {norms[-1]:.12e} "
+                f"{e[1].elapsed_time(e[2]) / 1e3:.2f}s (t+{time.time() - T_START:.0f}s)")
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -301,22 +412,22 @@ def run_gpu(args):
     _v = _C.c_double()
     ctx.call("tnr_get_counter", b"peer_scatter_launches", _C.byref(_v))
     peer_launches = int(_v.value)
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms = agree(dev_ms, e2e_ms)
     if rank == 0:
-        K = args.steps
+        K = k_done
         sec = dev_ms / 1e3 / K
         e2e_sec = e2e_ms / 1e3 / K
-        fl = step_flops(chi) if all(d == chi for d in scheme.T.dims) else None
+        fl = step_flops(chi) if saturated() else None
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        cpu_v, cpu_cores, cpu_sample_desc = (None, None, None)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        clock_peak = 148 * DMMA_FMA_PER_CLK_SM * 2 * sm_mhz * 1e6 / 1e12
+        cpu_v = cpu_cores = cpu_sample_desc = cpu_val = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_v, cpu_cores, cpu_sample_desc = cpu_sample(chi)
+            cpu_v, cpu_cores, cpu_sample_desc, cpu_val = cpu_sample(chi)
         out = {
             "metric": METRIC % chi, "value": sec, "unit": "s/RG-step", "n_gpus": world,
-            "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
+            "steps": K, "warmup": w_done, "steps_requested": args.steps,
+            "warmup_requested": args.warmup, "ms_per_step": dev_ms / K,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.engine == "dmma" else
             (f"f64 emulated by {args.ozaki_planes} int8 digit planes (Ozaki scheme, tcgen05 kind::i8)"
@@ -327,8 +438,14 @@ def run_gpu(args):
             "config": {
                 "engine": args.engine,
                 "workload": f"HOTRG_3D on classical_ising_3D(Trivial, beta_c) truncrank({chi}); "
-                            f"timed steps are RG iterations {args.warmup + 1}.."
-                            f"{args.warmup + K} of run! (legs {scheme.T.dims})",
+                            f"timed steps are RG iterations {first_iter}.."
+                            f"{first_iter + K - 1} of run! (legs {scheme.T.dims})",
+                "time_budget_s": budget,
+                "time_box": (f"{K} of {args.steps} requested timed steps and {w_done} of "
+                             f"{args.warmup} requested warm-up iterations fit the wall budget; "
+                             "all legs equal chi from RG iteration 3 on, so every timed step is "
+                             "a steady-state step") if (K < args.steps or w_done < args.warmup)
+                else "all requested steps ran",
                 "parallelism": "1 GPU" if world == 1 else
                 f"open x-bond sharded over {world} GPUs; exchange: " +
                 ("every T' slab stored to all ranks over NVLink by the kernel that produces it "
@@ -337,8 +454,10 @@ def run_gpu(args):
                 "l2": "inputs (chi^6 doubles = %.2f GB) exceed L2; no flush needed" %
                       (scheme.T.size * 8 / 1e9),
                 "steps_per_s": 1.0 / sec,
+                "step_flop": fl,
                 "step_tflops": (fl / sec / 1e12) if fl else None,
-                "step_frac_of_fp64_peak": (fl / sec / 1e12 / peak / world) if fl else None,
+                "step_frac_of_nominal_fp64_peak": (fl / sec / 1e12 / NOMINAL_FP64_TFLOPS / world)
+                if fl else None,
                 "norms_tail": norms[-min(3, len(norms)):],
                 # size-independent sanity at the full workload: free energy of the run so far
                 # (series sum_i log(z_i) 8^(1-i), remainder < 8^-n) against the value the
@@ -346,21 +465,26 @@ def run_gpu(args):
                 "free_energy": tk.free_energy(norms, tk.ising_βc_3D, scalefactor=8.0),
                 "free_energy_benchmark": -3.507,
                 "wall_s_timed_region": wall,
-                # not measured in this run: the opt-in INT8 emulation engine, for context
-                "experimental_ozaki_engine": None if args.engine == "ozaki" else {
-                    "s_per_rg_step_n1_chi24": 146.0,
-                    "how": "python bench.py --engine ozaki (separate run, same B200 pool)",
-                    "source": "profiles/r01_bench_n1_chi24_ozaki_experimental.json"},
+                "wall_s_since_start": time.time() - T_START,
+                "cpu_flop_model_validation": cpu_val,
             },
             "roofline": {
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE 13824^3 launch of this
-                # kernel (ncu --set full, gpurun_out/prof_gemm_tma_13824_r01.ncu-rep, summarised
-                # in profiles/r01_summary.md): 32.13 GB + 1.53 GB for 4.59 GB of operand+result
-                # bytes (operands re-read from L2, hit rate 81 %); 227 GB/s, 3 % of HBM
-                "traffic": 33.66e9 if (chi == 24 and args.engine == "dmma") else None,
-                "traffic_unit": "bytes per launch",
+                "bound": "tensor", "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS,
+                "unit": "TFLOP/s",
+                "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
+                "peak_source": "of NOMINAL: B200 FP64 tensor peak 40 TFLOP/s (vendor figure); "
+                               "MEASURED_PEAKS.json and B200_PROFILING.md hold no FP64 number",
+                "frac_of_clock_derived_peak": (achieved / clock_peak) if achieved else None,
+                "clock_derived_peak": clock_peak,
+                "clock_derived_how": f"148 SM x 64 FP64 FMA/clk (DMMA.8x8x4 pipe) x 2 x "
+                                     f"{sm_mhz:.0f} MHz (median SM clock sampled in this run)",
+                "frac_of_cublas_dgemm": (achieved / cublas) if achieved and cublas else None,
+                "cublas_dgemm_tflops": cublas,
+                "cublas_how": "torch.matmul FP64 8192^3, best of 5, measured in this process "
+                              "before the run (context only)",
+                # dram bytes of one launch are an ncu quantity and are not measured by this
+                # run: see profiles/ (ncu --set full raw export of this kernel)
+                "traffic": None,
                 "kernel": ("gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
                            "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
                            "projector Gram GEMMs above 1e11 flop)") if args.engine == "dmma" else
@@ -369,9 +493,6 @@ def run_gpu(args):
                            "against the FP64 peak may exceed 1) + DMMA kernels for the Gram GEMMs"),
                 "launches_timed": gemm_n,
                 "tma_gemm_launches": ctr.get("tma_gemm_launches"),
-                "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (of measured; "
-                               "MEASURED_PEAKS.json holds no FP64 figure); nominal FP64 tensor "
-                               "peak 40 TFLOP/s",
             },
             "cpu_baseline": {"value": cpu_v, "unit": "s/RG-step", "cores": cpu_cores,
                              "kind": "port", "sample": cpu_sample_desc},
@@ -388,9 +509,12 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chi", type=int, default=24)
+    ap.add_argument("--time-budget", type=float, default=780.0,
+                    help="wall seconds from interpreter start within which the run must end "
+                         "(0 = run exactly --steps / --warmup)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--crt-moduli", type=int, default=16)
