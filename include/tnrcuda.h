@@ -49,14 +49,16 @@ int tnr_reset_counters(tnr_context* ctx);
 /* counters of the warp-specialised TMA GEMM (subset of gemm_launches) */
 int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
 /* any counter by name: "launches", "gemm_launches", "grouped_gemm_launches",
- * "tma_gemm_launches", "gemm_flops", "permute_bytes" */
+ * "tma_gemm_launches", "gemm_flops", "permute_bytes", "permute_bulk_launches", ... */
 int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
 /* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests);
  * "disable_subspace", "disable_block_jacobi", "disable_precondition" switch the fast SVD/eigh
  * paths off; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes;
  * "ozaki_crt" = N (0 = off, default; 14..18) selects its CRT variant with N moduli instead;
- * "permute_unroll" = 1 (default) | 2 | 4 and "permute_tile" = 32 | 48 | 64 | 96 (default) select
- * variants of the permute kernels.  Unknown keys and out-of-range values are errors. */
+ * "permute_bulk" = 1 (default) | 0: the TMA-fed tiled copy kernel (cp.async.bulk reads) for every
+ * strided copy whose source pieces are 16-byte aligned; "permute_unroll" = 1 | 2 | 4 (default) and
+ * "permute_tile" = 32 | 48 | 64 | 96 (default) select variants of the fallback permute kernels.
+ * Unknown keys and out-of-range values are errors. */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
  * library stream; read returns the summed milliseconds, flops and the launch count. */

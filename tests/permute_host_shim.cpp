@@ -9,9 +9,54 @@
 
 using namespace tnr;
 
+// the bulk kernel's two phases: every "thread" issues its pieces (memcpy stands in for
+// cp.async.bulk and CHECKS the 16-byte rules of the instruction), then the write phase runs
+static int run_bulk(const double* src, double* dst, const BulkPlan& bp, long long* info) {
+    const BulkParams& p = bp.p;
+    info[0] = (long long)p.TI1 * p.TI2 * p.TV; info[1] = (long long)p.TJ1 * p.TJ2 * p.TV;
+    info[2] = bp.blocks; info[3] = (long long)bp.smem; info[4] = p.pitch; info[5] = p.vec;
+    std::vector<double> storage(bp.smem / sizeof(double) + 2);
+    double* tile_buf = storage.data();
+    if ((uintptr_t)tile_buf % 16) ++tile_buf;
+    int bad = 0;
+    for (long long b = 0; b < bp.blocks; ++b) {
+        std::fill(storage.begin(), storage.end(), -12345.678);
+        BulkGeom g = bulk_geometry(src, dst, p, b);
+        long long bytes = 0;
+        auto issue = [&](double* tp, const double* sp, int nbytes) {
+            if (nbytes <= 0 || nbytes % 16 || (uintptr_t)tp % 16 || (uintptr_t)sp % 16) ++bad;
+            std::memcpy(tp, sp, (size_t)nbytes);
+            bytes += nbytes;
+        };
+        for (int tid = 0; tid < 256; ++tid) bulk_load_phase(g, p, tile_buf, tid, 256, issue);
+        if (bytes != bulk_tile_bytes(g)) ++bad;      // the mbarrier's expect_tx count
+        auto st1 = [&](double* gp, const double* t) { *gp = *t; };
+        auto st2 = [&](double* gp, const double* t) {
+            if ((uintptr_t)gp % 16 || (uintptr_t)t % 16) ++bad;
+            gp[0] = t[0]; gp[1] = t[1];
+        };
+        for (int tid = 0; tid < 256; ++tid) {
+            if (p.vec == 2) bulk_write_phase<2>(g, p, tile_buf, tid, st2);
+            else bulk_write_phase<1>(g, p, tile_buf, tid, st1);
+        }
+    }
+    return bad ? -3 : 4;
+}
+
 static int run_plan(const double* src, double* dst, int rank, const long long* dims,
                     const long long* sst, const long long* dst_st, int unroll, int tile,
                     long long* info) {
+    if (unroll < 0) {   // bulk path requested: kind 4 when the planner accepts, else fall through
+        long long total = 1;
+        for (int i = 0; i < rank; ++i) total *= dims[i];
+        auto m = merged_groups(rank, dims, sst, dst_st);
+        const bool flat = m.empty() || (m.size() == 1 && m[0].s == 1 && m[0].d == 1);
+        if (total > 0 && !flat) {
+            BulkPlan bp = plan_bulk_copy(m, (uintptr_t)src, (uintptr_t)dst, tile);
+            if (bp.ok) return run_bulk(src, dst, bp, info);
+        }
+        unroll = 1;
+    }
     CopyPlan plan = plan_strided_copy(rank, dims, sst, dst_st, tile);
     if (plan.error) return -1;
     const CopyParams& p = plan.p;

@@ -151,9 +151,10 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             ctx->c.permute_tile = (int)value;
         }
         else if (std::strcmp(key, "permute_unroll") == 0) {
-            TNR_CHECK(value == 1 || value == 2 || value == 4, "permute_unroll: 1 (default), 2 or 4");
+            TNR_CHECK(value == 1 || value == 2 || value == 4, "permute_unroll: 1, 2 or 4 (default)");
             ctx->c.permute_unroll = (int)value;
         }
+        else if (std::strcmp(key, "permute_bulk") == 0) ctx->c.permute_bulk = value != 0;
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
@@ -622,6 +623,7 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "ozaki_launches") *value = (double)c.ozaki_launches;
         else if (n == "ozaki_gemms") *value = (double)c.ozaki_gemms;
         else if (n == "peer_scatter_launches") *value = (double)c.peer_scatter_launches;
+        else if (n == "permute_bulk_launches") *value = (double)c.permute_bulk_launches;
         else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;

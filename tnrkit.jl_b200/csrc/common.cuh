@@ -38,6 +38,7 @@ struct Counters {
     unsigned long long ozaki_launches = 0;   // INT8 tcgen05 group kernels
     unsigned long long ozaki_gemms = 0;      // FP64-equivalent GEMMs served by the Ozaki engine
     unsigned long long peer_scatter_launches = 0;  // slab scatters that also stored to peer GPUs
+    unsigned long long permute_bulk_launches = 0;  // strided copies served by the TMA-fed kernel
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
@@ -58,7 +59,8 @@ struct Context {
     bool disable_subspace = false;  // force full Jacobi in eigh_trunc
     bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
     int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
-    int permute_unroll = 1;  // 2 | 4: permute kernels with several loads in flight per thread (opt-in)
+    int permute_unroll = 4;  // 1 | 2 | 4: rows of the read phase in flight per thread in the fallback tiled kernel (r02: 4 measured 1.7x faster than 1)
+    bool permute_bulk = true;  // TMA-fed tiled copy (cp.async.bulk) whenever the source pieces are 16-byte aligned
     int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems

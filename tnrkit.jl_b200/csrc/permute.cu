@@ -99,6 +99,62 @@ __global__ void __launch_bounds__(256) copy_tiled_mlp_kernel(const double* __res
     tile_write_phase(g, p, tile, threadIdx.x);
 }
 
+// ---- bulk-async tiled copy --------------------------------------------------------------
+// The whole tile of a CTA is requested from the TMA engine at once (cp.async.bulk, one request
+// per contiguous source piece, completion counted in bytes on an mbarrier); nothing is staged
+// in registers, so 3 resident CTAs keep ~220 KB per SM in flight / in the write phase.  The
+// write phase (permute_plan.cuh: bulk_write_phase) stores runs along the destination.
+__device__ __forceinline__ unsigned bsmem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+struct BulkIssue {
+    unsigned bar;
+    __device__ __forceinline__ void operator()(double* tp, const double* sp, int bytes) const {
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+            ::"r"(bsmem_u32(tp)), "l"(sp), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+};
+struct Store1 {
+    __device__ __forceinline__ void operator()(double* g, const double* t) const { *g = *t; }
+};
+struct Store2 {
+    __device__ __forceinline__ void operator()(double* g, const double* t) const {
+        *reinterpret_cast<double2*>(g) = *reinterpret_cast<const double2*>(t);
+    }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict__ src,
+                                                        double* __restrict__ dst,
+                                                        const BulkParams p) {
+    extern __shared__ __align__(16) double tile[];
+    __shared__ unsigned long long bar_storage;
+    const unsigned bar = bsmem_u32(&bar_storage);
+    const BulkGeom g = bulk_geometry(src, dst, p, blockIdx.x);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                     ::"r"(bar), "r"((int)bulk_tile_bytes(g)) : "memory");
+    }
+    __syncthreads();
+    bulk_load_phase(g, p, tile, threadIdx.x, 256, BulkIssue{bar});
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BDONE;\n"
+        "bra BWAIT;\n"
+        "BDONE:\n"
+        "}\n" ::"r"(bar), "r"(0) : "memory");
+    if (VEC == 2) bulk_write_phase<2>(g, p, tile, threadIdx.x, Store2{});
+    else bulk_write_phase<1>(g, p, tile, threadIdx.x, Store1{});
+}
+
 // same fastest index on both sides: one thread per element, inner index fastest.  T = double2
 // (opt-in with "permute_unroll" > 1): the inner run is contiguous and even on both sides and every
 // other stride is even, so the copy is the same strided copy on 16-byte elements.
@@ -180,6 +236,29 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
     if (total == 0) return;
     ctx->ctr.permute_bytes += 16.0 * (double)total;
     CopyParams& p = plan.p;
+    if (plan.kind != COPY_FLAT && ctx->permute_bulk) {
+        // the TMA-fed kernel whenever the copy has 16-byte aligned source pieces
+        BulkPlan bp = plan_bulk_copy(merged_groups(rank, dims, sstride, dstride), (uintptr_t)src,
+                                     (uintptr_t)dst, ctx->permute_tile);
+        if (bp.ok) {
+            static bool bulk_configured = false;
+            if (!bulk_configured) {
+                TNR_CUDA(cudaFuncSetAttribute(copy_bulk_kernel<1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                TNR_CUDA(cudaFuncSetAttribute(copy_bulk_kernel<2>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                bulk_configured = true;
+            }
+            if (bp.p.vec == 2)
+                copy_bulk_kernel<2><<<(unsigned)bp.blocks, 256, bp.smem, ctx->stream>>>(src, dst, bp.p);
+            else
+                copy_bulk_kernel<1><<<(unsigned)bp.blocks, 256, bp.smem, ctx->stream>>>(src, dst, bp.p);
+            TNR_CUDA(cudaGetLastError());
+            ctx->ctr.launches++;
+            ctx->ctr.permute_bulk_launches++;
+            return;
+        }
+    }
     if (plan.kind == COPY_FLAT) {
         int vec = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
         long long work = vec ? (total + 1) / 2 : total;

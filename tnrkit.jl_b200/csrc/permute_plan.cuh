@@ -165,6 +165,290 @@ inline bool rows_vectorize(CopyParams& p, uintptr_t src_addr, uintptr_t dst_addr
     return true;
 }
 
+// merged index groups of a strided copy in destination order (the first step of both planners)
+struct BulkGroup { long long n, s, d; };
+inline std::vector<BulkGroup> merged_groups(int rank, const long long* dims,
+                                            const long long* sstride, const long long* dstride) {
+    std::vector<BulkGroup> v, m;
+    for (int i = 0; i < rank; ++i)
+        if (dims[i] != 1) v.push_back({dims[i], sstride[i], dstride[i]});
+    std::stable_sort(v.begin(), v.end(),
+                     [](const BulkGroup& a, const BulkGroup& b) { return a.d < b.d; });
+    for (auto& x : v) {
+        if (!m.empty() && m.back().s * m.back().n == x.s && m.back().d * m.back().n == x.d)
+            m.back().n *= x.n;
+        else
+            m.push_back(x);
+    }
+    return m;
+}
+
+// =====================================================================================
+// Bulk-async tiled copy (copy_bulk_kernel, csrc/permute.cu): the read side of a tile is done by
+// the TMA engine (cp.async.bulk global -> shared, SASS UBLKCP, completion on an mbarrier), so a
+// CTA has its whole tile (<= 72 KB) in flight without holding it in registers; the write side
+// is a per-thread phase with 16-byte stores where alignment allows.
+//
+// Index structure after merging:  v  = group that is fastest on BOTH sides (extent n_v, stride 1
+// on both sides; n_v = 1 for a true transposition), i' = (i1, i2) the groups that follow v in the
+// SOURCE, j' = (j1, j2) the groups that follow v in the DESTINATION, the rest are outer dims.
+// Shared-memory tile: [j'][i2][i1][v], row pitch `pitch` doubles (even, pitch/2 odd: rows start
+// 16-byte aligned for the bulk copies and the 16-byte row stride is odd in units of banks).
+// =====================================================================================
+constexpr int BULK_KMAX = 6;          // elements (of VEC doubles) per lane and output run
+constexpr int BULK_TILE_ELEMS = 9216; // doubles per tile (72 KB): 3 CTAs per SM
+
+struct BulkParams {
+    int rank;
+    long long dims[MAXR], ss[MAXR], ds[MAXR];
+    long long n_v, n_i1, n_i2, n_j1, n_j2;
+    long long s_i1, s_i2, s_j1, s_j2;
+    long long d_i1, d_i2, d_j1, d_j2;
+    int TV, TI1, TI2, TJ1, TJ2;
+    long long tiles_v, tiles_i1, tiles_i2, tiles_j1, tiles_j2;
+    int pitch;
+    int contig1, contig2;   // source row of a tile: (v,i1) contiguous / (v,i1,i2) contiguous
+    int vec;                // 2: 16-byte shared loads + global stores in the write phase, else 1
+    int R;                  // i1 rows written per warp pass (short destination runs are batched)
+};
+
+struct BulkPlan {
+    bool ok = false;
+    BulkParams p{};
+    long long blocks = 0;
+    size_t smem = 0;
+};
+
+inline int bulk_pick_extent(long long n, long long tgt, bool want_even) {
+    if (tgt < 1) tgt = 1;
+    if (n <= tgt) return (int)n;
+    for (long long t = tgt; 2 * t >= tgt && t >= 1; --t)
+        if (n % t == 0 && (!want_even || t % 2 == 0)) return (int)t;
+    if (want_even && tgt > 1 && tgt % 2) --tgt;
+    return (int)tgt;
+}
+
+// m: merged groups in destination order (m[0] destination-fastest).  Returns ok = false when
+// the copy does not have the structure / alignment the bulk kernel needs.
+inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_addr,
+                               uintptr_t dst_addr, int tile_tgt) {
+    BulkPlan out;
+    const size_t none = (size_t)-1;
+    if (m.empty() || m.size() > (size_t)MAXR + 4) return out;
+    if (src_addr % 16 != 0) return out;
+    BulkParams& p = out.p;
+    std::vector<bool> used(m.size(), false);
+    size_t iv = none;
+    if (m[0].s == 1 && m[0].d == 1) { iv = 0; used[0] = true; }
+    p.n_v = (iv != none) ? m[0].n : 1;
+    // i1: smallest source stride among the rest; j1: first of the rest in destination order
+    // (the destination-contiguous group keeps priority over a source continuation i2)
+    size_t i1 = none;
+    for (size_t i = 0; i < m.size(); ++i)
+        if (!used[i] && (i1 == none || m[i].s < m[i1].s)) i1 = i;
+    if (i1 == none) return out;                      // a flat copy: not ours
+    if (iv == none && m[i1].s != 1) return out;      // no unit-stride run in the source
+    used[i1] = true;
+    size_t j1 = none;
+    for (size_t i = 0; i < m.size(); ++i)
+        if (!used[i]) { j1 = i; break; }
+    if (j1 != none) used[j1] = true;
+    size_t i2 = none;
+    for (size_t i = 0; i < m.size(); ++i)
+        if (!used[i] && m[i].s == m[i1].s * m[i1].n) i2 = i;
+    if (i2 != none) used[i2] = true;
+    size_t j2 = none;
+    if (j1 != none)
+        for (size_t i = 0; i < m.size(); ++i)
+            if (!used[i] && m[i].d == m[j1].d * m[j1].n) j2 = i;
+    if (j2 != none) used[j2] = true;
+    auto G = [&](size_t k, long long& n, long long& s, long long& d) {
+        if (k == none) { n = 1; s = 0; d = 0; } else { n = m[k].n; s = m[k].s; d = m[k].d; }
+    };
+    G(i1, p.n_i1, p.s_i1, p.d_i1); G(i2, p.n_i2, p.s_i2, p.d_i2);
+    G(j1, p.n_j1, p.s_j1, p.d_j1); G(j2, p.n_j2, p.s_j2, p.d_j2);
+    p.rank = 0;
+    long long outer = 1;
+    for (size_t i = 0; i < m.size(); ++i) {
+        if (used[i]) continue;
+        if (p.rank >= MAXR) return out;
+        p.dims[p.rank] = m[i].n; p.ss[p.rank] = m[i].s; p.ds[p.rank] = m[i].d;
+        p.rank++;
+        outer *= m[i].n;
+    }
+    // ---- tile extents ----------------------------------------------------------------
+    const bool dst_even = dst_addr % 16 == 0 && p.d_i1 % 2 == 0 && p.d_i2 % 2 == 0 &&
+                          p.d_j1 % 2 == 0 && p.d_j2 % 2 == 0 && [&] {
+                              for (int d = 0; d < p.rank; ++d) if (p.ds[d] % 2) return false;
+                              return true; }();
+    const int run_max1 = 32 * BULK_KMAX;            // doubles per output run with 8-byte stores
+    if (p.n_v == 1) {
+        p.TV = 1;
+        const int tgt = std::min(tile_tgt, 96);
+        auto split = [&](long long n1, long long n2, int& T1, int& T2, bool even) {
+            if (n1 >= tgt) { T1 = bulk_pick_extent(n1, tgt, even); T2 = 1; }
+            else { T1 = (int)n1; T2 = n2 <= 1 ? 1 : bulk_pick_extent(n2, tgt / n1, false); }
+        };
+        split(p.n_i1, p.n_i2, p.TI1, p.TI2, true);
+        split(p.n_j1, p.n_j2, p.TJ1, p.TJ2, false);
+        p.vec = 1;
+    } else {
+        p.vec = (p.n_v % 2 == 0 && dst_even) ? 2 : 1;
+        const int run_max = run_max1 * p.vec;
+        p.TV = (p.n_v <= run_max) ? (int)p.n_v : bulk_pick_extent(p.n_v, run_max, true);
+        if (p.vec == 2 && p.TV % 2) p.vec = 1;
+        const long long tgt_j = std::max<long long>(1, (long long)(run_max1 * p.vec) / p.TV);
+        if (p.n_j1 >= tgt_j) { p.TJ1 = bulk_pick_extent(p.n_j1, tgt_j, false); p.TJ2 = 1; }
+        else { p.TJ1 = (int)p.n_j1;
+               p.TJ2 = p.n_j2 <= 1 ? 1 : bulk_pick_extent(p.n_j2, tgt_j / p.n_j1, false); }
+        const long long tgt_i = std::max<long long>(1, BULK_TILE_ELEMS /
+                                                    ((long long)p.TJ1 * p.TJ2 * p.TV));
+        if (p.n_i1 >= tgt_i) { p.TI1 = bulk_pick_extent(p.n_i1, tgt_i, false); p.TI2 = 1; }
+        else { p.TI1 = (int)p.n_i1;
+               p.TI2 = p.n_i2 <= 1 ? 1 : bulk_pick_extent(p.n_i2, tgt_i / p.n_i1, false); }
+    }
+    p.contig1 = (p.s_i1 == p.n_v && p.TV == p.n_v) ? 1 : 0;
+    p.contig2 = (p.contig1 && p.TI1 == p.n_i1 && (p.n_i2 == 1 || p.s_i2 == p.s_i1 * p.n_i1)) ? 1 : 0;
+    if (p.n_i2 == 1) p.contig2 = p.contig1;   // a single i2 slice: the row is the (v,i1) run
+    // ---- 16-byte rule of the bulk copies: every piece starts on an even element and has an
+    // even length, for full and ragged tiles alike ----------------------------------------
+    auto even = [](long long x) { return x % 2 == 0; };
+    if (p.contig1) {
+        // piece = TV*ti1 (* ti2): ti1 takes the values TI1 and n_i1 % TI1
+        if (!even(p.n_v * p.TI1) || !even(p.n_v * (p.n_i1 % p.TI1))) return out;
+    } else {
+        if (!even(p.TV) || !even(p.n_v % p.TV) || !even(p.s_i1)) return out;
+        if (p.TV * 8 < 64) return out;              // pieces below 64 bytes: not worth a bulk copy
+    }
+    if (!even(p.s_j1) || !even(p.s_j2)) return out;
+    if (p.n_i2 > 1 && !even(p.s_i2)) return out;
+    for (int d = 0; d < p.rank; ++d) if (!even(p.ss[d])) return out;
+    if ((long long)p.TJ1 * p.TJ2 * p.TV > (long long)run_max1 * p.vec) return out;
+    {   // rows per pass: about 96 (VEC = 1) / 192 (VEC = 2) doubles per warp pass
+        const long long run = (long long)p.TJ1 * p.TJ2 * p.TV;
+        long long R = (32LL * p.vec * 3) / run;
+        if (R < 1) R = 1;
+        if (R > p.TI1) R = p.TI1;
+        if (R * run > (long long)run_max1 * p.vec) R = std::max<long long>(1, ((long long)run_max1 * p.vec) / run);
+        p.R = (int)R;
+    }
+    p.tiles_v = (p.n_v + p.TV - 1) / p.TV;
+    p.tiles_i1 = (p.n_i1 + p.TI1 - 1) / p.TI1;
+    p.tiles_i2 = (p.n_i2 + p.TI2 - 1) / p.TI2;
+    p.tiles_j1 = (p.n_j1 + p.TJ1 - 1) / p.TJ1;
+    p.tiles_j2 = (p.n_j2 + p.TJ2 - 1) / p.TJ2;
+    long long row = (long long)p.TI1 * p.TI2 * p.TV;
+    long long pitch = row + (row & 1);
+    if ((pitch / 2) % 2 == 0) pitch += 2;
+    if (pitch > (1 << 20)) return out;
+    p.pitch = (int)pitch;
+    out.smem = (size_t)p.TJ1 * p.TJ2 * pitch * sizeof(double);
+    if (out.smem > 100 * 1024) return out;
+    out.blocks = p.tiles_v * p.tiles_i1 * p.tiles_i2 * p.tiles_j1 * p.tiles_j2 * outer;
+    if (out.blocks >= (1LL << 31) || out.blocks <= 0) return out;
+    out.ok = true;
+    return out;
+}
+
+struct BulkGeom {
+    const double* sp;
+    double* dp;
+    int tv, ti1, ti2, tj1, tj2, ci, cj;
+};
+
+TNR_HD BulkGeom bulk_geometry(const double* src, double* dst, const BulkParams& p, long long bid) {
+    long long t_v = bid % p.tiles_v; bid /= p.tiles_v;
+    long long t_i1 = bid % p.tiles_i1; bid /= p.tiles_i1;
+    long long t_i2 = bid % p.tiles_i2; bid /= p.tiles_i2;
+    long long t_j1 = bid % p.tiles_j1; bid /= p.tiles_j1;
+    long long t_j2 = bid % p.tiles_j2; bid /= p.tiles_j2;
+    long long soff = 0, doff = 0;
+#pragma unroll
+    for (int d = 0; d < MAXR; ++d) {
+        if (d < p.rank) {
+            long long i = bid % p.dims[d];
+            bid /= p.dims[d];
+            soff += i * p.ss[d];
+            doff += i * p.ds[d];
+        }
+    }
+    const long long v0 = t_v * p.TV, i10 = t_i1 * p.TI1, i20 = t_i2 * p.TI2, j10 = t_j1 * p.TJ1,
+                    j20 = t_j2 * p.TJ2;
+    BulkGeom g;
+    g.tv = (int)((p.n_v - v0 < p.TV) ? p.n_v - v0 : p.TV);
+    g.ti1 = (int)((p.n_i1 - i10 < p.TI1) ? p.n_i1 - i10 : p.TI1);
+    g.ti2 = (int)((p.n_i2 - i20 < p.TI2) ? p.n_i2 - i20 : p.TI2);
+    g.tj1 = (int)((p.n_j1 - j10 < p.TJ1) ? p.n_j1 - j10 : p.TJ1);
+    g.tj2 = (int)((p.n_j2 - j20 < p.TJ2) ? p.n_j2 - j20 : p.TJ2);
+    g.ci = g.ti1 * g.ti2;
+    g.cj = g.tj1 * g.tj2;
+    g.sp = src + soff + v0 + i10 * p.s_i1 + i20 * p.s_i2 + j10 * p.s_j1 + j20 * p.s_j2;
+    g.dp = dst + doff + v0 + i10 * p.d_i1 + i20 * p.d_i2 + j10 * p.d_j1 + j20 * p.d_j2;
+    return g;
+}
+
+TNR_HD long long bulk_tile_bytes(const BulkGeom& g) {
+    return (long long)g.cj * g.ci * g.tv * 8;
+}
+
+// load phase: the pieces of the tile are dealt round-robin to the threads; `issue(dst, src,
+// bytes)` is cp.async.bulk on the device and memcpy in the host check
+template <typename Issue>
+TNR_HD void bulk_load_phase(const BulkGeom& g, const BulkParams& p, double* tile, int tid,
+                            int nthreads, Issue issue) {
+    const int np1 = p.contig1 ? 1 : g.ti1;
+    const int np2 = p.contig2 ? 1 : g.ti2;
+    const int np = np1 * np2;
+    const int plen = g.tv * (p.contig1 ? g.ti1 : 1) * (p.contig2 ? g.ti2 : 1);
+    const int total = g.cj * np;
+    for (int q = tid; q < total; q += nthreads) {
+        const int r = q / np, pc = q - r * np;
+        const int a1 = pc % np1, a2 = pc / np1;
+        const int j1 = r % g.tj1, j2 = r / g.tj1;
+        const double* sp = g.sp + j1 * p.s_j1 + j2 * p.s_j2 + a1 * p.s_i1 + a2 * p.s_i2;
+        double* tp = tile + (long long)r * p.pitch + (a2 * g.ti1 + a1) * g.tv;
+        issue(tp, sp, plen * 8);
+    }
+}
+
+// write phase: a warp pass writes R consecutive i1 rows of the tile (same i2); the lanes run
+// along (row, destination run (j2, j1, v)) of the pass, VEC doubles per lane and access
+template <int VEC, typename Store>
+TNR_HD void bulk_write_phase(const BulkGeom& g, const BulkParams& p, const double* tile, int tid,
+                             Store store) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int run = g.cj * g.tv;
+    const int R = p.R;
+    int so[BULK_KMAX], ri[BULK_KMAX];
+    long long dof[BULK_KMAX];
+#pragma unroll
+    for (int k = 0; k < BULK_KMAX; ++k) {
+        const int e = (lane + 32 * k) * VEC;
+        so[k] = -1;
+        ri[k] = 0;
+        dof[k] = 0;
+        if (e < R * run) {
+            const int rr = e / run, x = e - rr * run;
+            const int jj = x / g.tv, v = x - jj * g.tv;
+            const int j1 = jj % g.tj1, j2 = jj / g.tj1;
+            ri[k] = rr;
+            so[k] = jj * p.pitch + rr * g.tv + v;
+            dof[k] = rr * p.d_i1 + j1 * p.d_j1 + j2 * p.d_j2 + v;
+        }
+    }
+    const int blocks1 = (g.ti1 + R - 1) / R;          // passes per i2 slice
+    const int passes = blocks1 * g.ti2;
+    for (int q = warp; q < passes; q += 8) {
+        const int i2 = q / blocks1, i10 = (q - i2 * blocks1) * R;
+        const int left = g.ti1 - i10;
+        double* gp = g.dp + i10 * p.d_i1 + i2 * p.d_i2;
+        const double* t = tile + (i2 * g.ti1 + i10) * g.tv;
+#pragma unroll
+        for (int k = 0; k < BULK_KMAX; ++k)
+            if (so[k] >= 0 && ri[k] < left) store(gp + dof[k], t + so[k]);
+    }
+}
+
 // ---- per-thread phases of the tiled kernel with U rows of loads in flight -------------------
 struct TileGeom {
     const double* sp;

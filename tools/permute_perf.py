@@ -15,11 +15,16 @@ cases = [("rotate ((6,4),(2,3,1,5))", (chi,) * 6, (5, 3, 1, 2, 0, 4)),
          ("Qn -> Qk", (chi,) * 6, (1, 3, 5, 0, 2, 4)),
          ("Gram operand [K|z x]", (chi,) * 6, (1, 2, 3, 4, 0, 5)),
          ("matrix transpose", (chi ** 3, chi ** 3), (1, 0)),
+         ("tall transpose chi^4 x chi^2", (chi ** 4, chi ** 2), (1, 0)),
+         ("ATRG_3D ((4,1),(2,3))-like", (chi,) * 6, (3, 0, 1, 2, 5, 4)),
          ("flat copy", (chi ** 6,), (0,))]
-for unroll, tile in [(1, 96), (2, 96), (4, 96), (4, 64), (4, 48), (1, 48), (4, 32)]:
+variants = [(1, 4, 96), (0, 4, 96), (0, 1, 96)] if len(sys.argv) < 3 else \
+    [(0, 1, 96), (0, 2, 96), (0, 4, 96), (0, 4, 64), (0, 4, 48), (0, 1, 48), (0, 4, 32)]
+for bulk, unroll, tile in variants:
+    ctx.set_option("permute_bulk", bulk)
     ctx.set_option("permute_unroll", unroll)
     ctx.set_option("permute_tile", tile)
-    print(f"--- permute_unroll = {unroll}, permute_tile = {tile}", flush=True)
+    print(f"--- permute_bulk = {bulk}, permute_unroll = {unroll}, permute_tile = {tile}", flush=True)
     for name, dims, perm in cases:
         n = 1
         for d in dims: n *= d
@@ -28,11 +33,13 @@ for unroll, tile in [(1, 96), (2, 96), (4, 96), (4, 64), (4, 48), (1, 48), (4, 3
         def run():
             ctx.call("tnr_permute", src.data_ptr(), dst.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
         run(); torch.cuda.synchronize()
-        if (unroll, tile) != (1, 96):   # same bits as the default kernels
+        if (bulk, unroll, tile) != (0, 1, 96):   # same bits as the round-1 kernels
+            ctx.set_option("permute_bulk", 0)
             ctx.set_option("permute_unroll", 1)
             ctx.set_option("permute_tile", 96)
             ref = torch.empty_like(src)
             ctx.call("tnr_permute", src.data_ptr(), ref.data_ptr(), len(dims), _lib.i64(dims), _lib.i32(perm))
+            ctx.set_option("permute_bulk", bulk)
             ctx.set_option("permute_unroll", unroll)
             ctx.set_option("permute_tile", tile)
             torch.cuda.synchronize()
@@ -44,5 +51,6 @@ for unroll, tile in [(1, 96), (2, 96), (4, 96), (4, 64), (4, 48), (1, 48), (4, 3
             e0.record(); run(); e1.record(); e1.synchronize()
             best = min(best, e0.elapsed_time(e1))
         print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
-ctx.set_option("permute_unroll", 1)
+ctx.set_option("permute_bulk", 1)
+ctx.set_option("permute_unroll", 4)
 ctx.set_option("permute_tile", 96)
