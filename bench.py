@@ -406,12 +406,16 @@ def run_gpu(args):
     dev_ms = sum(e[1].elapsed_time(e[2]) for e in ev)
     e2e_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
     gemm_ms, gemm_fl, gemm_n = ctx.gemm_timing_read()
-    ctx.gemm_timing(False)
     ctr = ctx.counters()
     import ctypes as _C
     _v = _C.c_double()
     ctx.call("tnr_get_counter", b"peer_scatter_launches", _C.byref(_v))
     peer_launches = int(_v.value)
+    phases = {}
+    for nm in ("hotrg3d.projectors", "hotrg3d.pk_build", "hotrg3d.q_build", "hotrg3d.uy_scatter"):
+        ctx.call("tnr_get_counter", ("phase_ms." + nm).encode(), _C.byref(_v))
+        phases[nm] = _v.value
+    ctx.gemm_timing(False)
     dev_ms, e2e_ms = agree(dev_ms, e2e_ms)
     if rank == 0:
         K = k_done
@@ -467,6 +471,10 @@ def run_gpu(args):
                 "wall_s_timed_region": wall,
                 "wall_s_since_start": time.time() - T_START,
                 "cpu_flop_model_validation": cpu_val,
+                # CUDA-event time of the phases of the z-compressions on rank 0, per RG step
+                # (the chunk GEMM is `roofline`; projectors are dealt to the ranks when N > 1)
+                "phases_s_per_step": {k: v / 1e3 / K for k, v in phases.items()},
+                "chunk_gemm_s_per_step": gemm_ms / 1e3 / K,
             },
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS,

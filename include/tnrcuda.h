@@ -58,6 +58,9 @@ int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
  * "permute_bulk" = 1 (default) | 0: the TMA-fed tiled copy kernel (cp.async.bulk reads) for every
  * strided copy whose source pieces are 16-byte aligned; "permute_unroll" = 1 | 2 | 4 (default) and
  * "permute_tile" = 32 | 48 | 64 | 96 (default) select variants of the fallback permute kernels.
+ * "permute_tpc" (1..8) and "permute_chunk_below" (bytes) tune the TMA-fed copy;
+ * "hotrg3d_pk_budget_mb": megabytes of absorbed operands Pk_d the HOTRG_3D z-compression holds
+ * at once (default 49152; the d loop is blocked into windows, also capped by the free memory).
  * Unknown keys and out-of-range values are errors. */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
@@ -196,6 +199,23 @@ int tnr_hotrg3d_substep(tnr_context* ctx, const double* T, const int64_t* dims, 
 int tnr_hotrg3d_substep_peers(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
                               double* const* Tout_peers, int npeers, int self, int64_t* dims_out,
                               int64_t f_begin, int64_t f_end);
+/* The two halves of _step!(::HOTRG_3D) as separate entries, so that the N ranks of a sharded run
+ * do not all repeat the projector work (the replicated part that limited scaling in round 1).
+ * tnr_hotrg3d_proj_half: ONE of the four truncated eigendecompositions of
+ * _get_hotrg3d_xproj / _yproj (src/schemes/hotrg3d.jl:83-108): which = 0: x-bond, MM^dagger
+ * (_get_MMdag_3d, :47-66); 1: x-bond, M^dagger M (_get_MdagM_3d, :68-87); 2 / 3: the same for the
+ * y-bond (after the permutation of :103-108).  Writes U (n x k, column major, n = D^2,
+ * k = min(chi, n)) followed by the truncation error eps (one double) to `out` (n*k + 1 doubles,
+ * device memory).  Ranks compute different halves and exchange the packed results (broadcast).
+ * tnr_hotrg3d_contract: hotrg3d.jl:116-120 for the slices f_begin <= f < f_end with the four
+ * packed halves given back to back in `halves` (x-left, x-right, y-left, y-right); the choice
+ * `(eps > eps') ? U' : U` of hotrg3d.jl:96 is made on the device.  `Tout_peers` / `npeers` /
+ * `self` as in tnr_hotrg3d_substep_peers (npeers = 1: a single local buffer). */
+int tnr_hotrg3d_proj_half(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                          int which, double* out);
+int tnr_hotrg3d_contract(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                         const double* halves, double* const* Tout_peers, int npeers, int self,
+                         int64_t* dims_out, int64_t f_begin, int64_t f_end);
 /* step!(::ATRG_3D, trunc)           src/schemes/atrg3d.jl:85-97 */
 int tnr_atrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
                     int64_t* dims_out);

@@ -92,3 +92,40 @@ class TRG_sym:
         self.last_spectra = (sp1, sp2)
 
     finalize = o.TRG.finalize
+
+
+class BTRG_sym:
+    """BTRG (src/schemes/btrg.jl:62-97) with TensorKit's symmetric svd_trunc semantics: the two
+    truncated SVDs of `step!` are done sector by sector with a sector-global truncrank; bond
+    weights, contraction and finalize! are tnr_oracle.BTRG's."""
+
+    def __init__(self, T, charges, signs, N, k=-0.5):
+        self.T = np.array(T, dtype=float)
+        self.charges = [list(c) for c in charges]
+        self.signs = list(signs)
+        self.N = N
+        self.k = k
+        self.S1 = np.eye(self.T.shape[1])
+        self.S2 = np.eye(self.T.shape[0])
+        self.last_spectra = None
+
+    def step(self, chi):
+        T, ch, sg, N, k = self.T, self.charges, self.signs, self.N, self.k
+        U, S, V, _, sp1, b1 = sector_svd_trunc(T, 2, chi, ch, sg, N)
+        Sa, Sb = o.pseudopow(S, (1 - k) / 2), o.pseudopow(S, k)
+        A, B, S1n = U * Sa, Sa[:, None, None] * V, np.diag(Sb)
+        perm = (2, 0, 3, 1)                                     # ((3,1),(4,2)), btrg.jl:75
+        U, S, V, _, sp2, b2 = sector_svd_trunc(np.transpose(T, perm), 2, chi,
+                                               [ch[p] for p in perm], [sg[p] for p in perm], N)
+        Sa, Sb = o.pseudopow(S, (1 - k) / 2), o.pseudopow(S, k)
+        C, D, S2n = U * Sa, Sa[:, None, None] * V, np.diag(Sb)
+        self.T = np.einsum("aqt,it,bik,kj,ujd,uo,poc,qp->abcd",
+                           D, self.S1, B, self.S2, C, self.S1, A, self.S2, optimize=o._OPT)
+        self.S1, self.S2 = S1n, S2n
+        # new legs: a = bond of D (V of the 2nd SVD, +), b = bond of B (V of the 1st, +),
+        #           c = bond of A (U of the 1st, -), d = bond of C (U of the 2nd, -)
+        self.charges = [b2, b1, b1, b2]
+        self.signs = [1, 1, -1, -1]
+        self.last_spectra = (sp1, sp2)
+
+    finalize = o.BTRG.finalize

@@ -19,25 +19,45 @@ static int run_bulk(const double* src, double* dst, const BulkPlan& bp, long lon
     double* tile_buf = storage.data();
     if ((uintptr_t)tile_buf % 16) ++tile_buf;
     int bad = 0;
+    const long long tile_elems = bulk_tile_elems(p);
+    if ((size_t)(tile_elems * p.tpc) * sizeof(double) != bp.smem || p.tpc < 1 || p.tpc > BULK_MAX_TPC)
+        return -4;
+    info[2] = p.ntiles;
     for (long long b = 0; b < bp.blocks; ++b) {
         std::fill(storage.begin(), storage.end(), -12345.678);
-        BulkGeom g = bulk_geometry(src, dst, p, b);
-        long long bytes = 0;
-        auto issue = [&](double* tp, const double* sp, int nbytes) {
-            if (nbytes <= 0 || nbytes % 16 || (uintptr_t)tp % 16 || (uintptr_t)sp % 16) ++bad;
-            std::memcpy(tp, sp, (size_t)nbytes);
-            bytes += nbytes;
-        };
-        for (int tid = 0; tid < 256; ++tid) bulk_load_phase(g, p, tile_buf, tid, 256, issue);
-        if (bytes != bulk_tile_bytes(g)) ++bad;      // the mbarrier's expect_tx count
-        auto st1 = [&](double* gp, const double* t) { *gp = *t; };
-        auto st2 = [&](double* gp, const double* t) {
-            if ((uintptr_t)gp % 16 || (uintptr_t)t % 16) ++bad;
-            gp[0] = t[0]; gp[1] = t[1];
-        };
-        for (int tid = 0; tid < 256; ++tid) {
-            if (p.vec == 2) bulk_write_phase<2>(g, p, tile_buf, tid, st2);
-            else bulk_write_phase<1>(g, p, tile_buf, tid, st1);
+        const long long t0 = b * p.tpc;
+        const int nt = (int)std::min<long long>(p.tpc, p.ntiles - t0);
+        // load phase of every tile of the CTA first, then the write phases (the kernel's order)
+        for (int t = 0; t < nt; ++t) {
+            BulkGeom g = bulk_geometry(src, dst, p, t0 + t);
+            long long bytes = 0;
+            auto issue = [&](double* tp, const double* sp, int nbytes) {
+                if (nbytes <= 0 || nbytes % 16 || (uintptr_t)tp % 16 || (uintptr_t)sp % 16) ++bad;
+                std::memcpy(tp, sp, (size_t)nbytes);
+                bytes += nbytes;
+            };
+            auto issue16 = [&](double* tp, const double* sp) { issue(tp, sp, 16); };
+            double* tb = tile_buf + t * tile_elems;
+            for (int tid = 0; tid < 256; ++tid) {
+                if (p.chunked) bulk_load_phase_chunked(g, p, tb, tid, 256, issue16);
+                else bulk_load_phase(g, p, tb, tid, 256, issue);
+            }
+            if (bytes != bulk_tile_bytes(g)) ++bad;      // the mbarrier's expect_tx count
+        }
+        for (int t = 0; t < nt; ++t) {
+            BulkGeom g = bulk_geometry(src, dst, p, t0 + t);
+            const double* tb = tile_buf + t * tile_elems;
+            auto st1 = [&](double* gp, const double* tt) { *gp = *tt; };
+            auto st2 = [&](double* gp, const double* tt) {
+                if ((uintptr_t)gp % 16 || (uintptr_t)tt % 16) ++bad;
+                gp[0] = tt[0]; gp[1] = tt[1];
+            };
+            for (int tid = 0; tid < 256; ++tid) {
+                BulkLaneTab tab;
+                bulk_lane_table(p, g.tv, g.tj1, g.cj, tid & 31, p.vec, tab);
+                if (p.vec == 2) bulk_write_phase<2>(g, p, tb, tid >> 5, tab, st2);
+                else bulk_write_phase<1>(g, p, tb, tid >> 5, tab, st1);
+            }
         }
     }
     return bad ? -3 : 4;

@@ -1,0 +1,49 @@
+"""CPU checks of tests/golden/baseline_sizes.json (the fixtures of tests/test_gpu_baseline_sizes.py):
+every case the device suite uses is present, was produced at the size it claims, carries its
+conditioning record, and its small-size sibling is reproduced by the oracle live."""
+import json
+import os
+
+import numpy as np
+
+import tnr_oracle as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NAMES = ["HOTRG_ising_trivial_chi64_it4", "TRG_ising_z2_chi128_it4", "BTRG_ising_z2_chi128_it4",
+         "TRG_potts_z3_chi128_it4", "BTRG_potts_z3_chi128_it4", "HOTRG_3D_ising_trivial_chi10_it6",
+         "HOTRG_3D_ising_trivial_chi12_it6", "ATRG_3D_ising_trivial_chi10_it5",
+         "ATRG_3D_ising_trivial_chi16_it4"]
+
+
+def _gold():
+    with open(os.path.join(HERE, "golden", "baseline_sizes.json")) as f:
+        return json.load(f)
+
+
+def test_fixture_file_is_complete_and_well_conditioned():
+    gold = _gold()
+    for name in NAMES:
+        g = gold[name]
+        assert g["valid"] and g["sensitivity_1e-14"] <= 1e-11, name
+        assert len(g["norms"]) == g["n"] + 1 and all(np.isfinite(g["norms"])), name
+        if "chi128" in name:
+            assert g["dims"] == [128] * 4 and len(g["spectra"]) == 2, name
+            for one in g["spectra"]:
+                assert sum(len(v) for _, v in one) == 128, name      # sector-global truncrank
+        if "chi64" in name:
+            assert g["dims"] == [64] * 4, name
+
+
+def test_first_norms_of_the_fixtures_are_the_live_oracle(tk):
+    """The first three RG steps are cheap: the recorded lists start with what the oracle gives
+    now (guards against a stale or hand-edited fixture)."""
+    gold = _gold()
+    live = o.run(o.HOTRG(np.asarray(tk.classical_ising(tk.Trivial))), 64, 2)
+    assert np.allclose(gold["HOTRG_ising_trivial_chi64_it4"]["norms"][:3], live, rtol=1e-12)
+    live = o.run(o.HOTRG_3D(np.asarray(tk.classical_ising_3D(tk.Trivial))), 10, 2)
+    assert np.allclose(gold["HOTRG_3D_ising_trivial_chi10_it6"]["norms"][:3], live, rtol=1e-12)
+    import sym_oracle as so
+
+    T = tk.classical_ising()
+    live = o.run(so.TRG_sym(np.asarray(T), T.charges, T.signs, 2), 128, 2)
+    assert np.allclose(gold["TRG_ising_z2_chi128_it4"]["norms"][:3], live, rtol=1e-12)

@@ -1,0 +1,89 @@
+"""Parity AT THE SIZES BASELINE.json NAMES (VERDICT r01 task 3): the device run against oracle
+outputs recorded in tests/golden/baseline_sizes.json by tests/golden/make_golden_baseline_sizes.py
+(the oracle needs minutes to an hour for these on the host, so they are fixtures, not live runs).
+
+  configs[1]  HOTRG, 2D Ising Trivial, truncrank(64): 4 steps (step 4 works on chi = 64 legs)
+  configs[2]  TRG / BTRG on classical_ising(Z2Irrep) and classical_potts(ZNIrrep{3}) at
+              truncrank(128): 4 steps (step 4 decomposes 16384 x 16384 matrices sector by sector);
+              norm lists AND the retained per-sector singular-value spectra of the last step
+  3D          HOTRG_3D chi = 10 / 12 (6 steps), ATRG_3D chi = 10 / 16: the largest bond dimensions
+              the dense numpy oracle can hold
+
+Tolerance: 1e-10 relative (north star) on every norm and on the retained spectra relative to
+the largest singular value.  Each fixture carries the oracle's own sensitivity to a 1e-14
+perturbation of the input; a case recorded as ill conditioned ("valid": false) is REFUSED here
+(tests/conditioning.py), it does not silently pass."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "baseline_sizes.json")) as _f:
+    GOLD = json.load(_f)
+
+
+def _case(name):
+    if name not in GOLD:
+        pytest.fail(f"fixture {name} missing: run tests/golden/make_golden_baseline_sizes.py {name}")
+    g = GOLD[name]
+    assert g["valid"], (f"{name}: the oracle's norm list moves by {g['sensitivity_1e-14']:.1e} under "
+                        "a 1e-14 perturbation -- not a parity case, pick another chi")
+    return g
+
+
+def _cmp_norms(got, g):
+    ref = np.array(g["norms"])
+    got = np.array(got)
+    assert got.shape == ref.shape
+    err = np.max(np.abs(got - ref) / np.abs(ref))
+    assert err <= RTOL, err
+
+
+def test_hotrg_chi64_configs1(tk):
+    g = _case("HOTRG_ising_trivial_chi64_it4")
+    s = tk.HOTRG(tk.classical_ising(tk.Trivial))
+    got = tk.run(s, tk.truncrank(g["chi"]), tk.maxiter(g["n"]), verbosity=0)
+    assert tuple(s.T.dims) == tuple(g["dims"]) == (64, 64, 64, 64)
+    _cmp_norms(got, g)
+
+
+@pytest.mark.parametrize("name,scheme,model", [
+    ("TRG_ising_z2_chi128_it4", "TRG", "ising"), ("BTRG_ising_z2_chi128_it4", "BTRG", "ising"),
+    ("TRG_potts_z3_chi128_it4", "TRG", "potts"), ("BTRG_potts_z3_chi128_it4", "BTRG", "potts")])
+def test_block_sparse_chi128_configs2(tk, ctx, name, scheme, model):
+    from tnrkit.jl_b200 import symmetric
+
+    g = _case(name)
+    T = tk.classical_ising() if model == "ising" else tk.classical_potts(3)
+    s = getattr(tk, scheme)(T)
+    assert s.sym
+    before = ctx.counters()["grouped_gemm_launches"]
+    got = tk.run(s, tk.truncrank(g["chi"]), tk.maxiter(g["n"]), verbosity=0)
+    assert ctx.counters()["grouped_gemm_launches"] > before      # one grouped launch per contraction
+    assert tuple(s.T.dims) == tuple(g["dims"]) == (128, 128, 128, 128)
+    _cmp_norms(got, g)
+    # retained spectra of the two truncated SVDs of the last step, sector by sector
+    spectra = symmetric.LAST_SPECTRA[scheme.lower()]
+    assert len(spectra) == len(g["spectra"]) == 2
+    for S_gpu, sp_ref in zip(spectra, g["spectra"]):
+        assert sorted(S_gpu) == [c for c, _ in sp_ref]                 # same sectors kept
+        top = max(max(v) for _, v in sp_ref)
+        for c, vals in sp_ref:
+            got_c = S_gpu[c].to_numpy()
+            assert got_c.shape == (len(vals),)                         # same multiplicity per sector
+            assert np.abs(got_c - np.array(vals)).max() <= RTOL * top
+
+
+@pytest.mark.parametrize("name,scheme", [
+    ("HOTRG_3D_ising_trivial_chi10_it6", "HOTRG_3D"), ("HOTRG_3D_ising_trivial_chi12_it6", "HOTRG_3D"),
+    ("ATRG_3D_ising_trivial_chi10_it5", "ATRG_3D"), ("ATRG_3D_ising_trivial_chi16_it4", "ATRG_3D")])
+def test_3d_schemes_largest_oracle_sizes(tk, name, scheme):
+    g = _case(name)
+    kw = {"shard": False} if scheme == "HOTRG_3D" else {}
+    s = getattr(tk, scheme)(tk.classical_ising_3D(tk.Trivial), **kw)
+    got = tk.run(s, tk.truncrank(g["chi"]), tk.maxiter(g["n"]), verbosity=0)
+    _cmp_norms(got, g)

@@ -45,6 +45,11 @@ def _worker(rank, world, port, chi, nsteps, q):
         v1 = C.c_double()
         ctx.call("tnr_get_counter", b"peer_scatter_launches", C.byref(v1))
         out[mode + "_peer_launches"] = v1.value - v0.value
+    # round-1 behaviour (every rank repeats the projector work) and the single-GPU run
+    s = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), split_projectors=False)
+    out["replicated_projectors"] = tk.run(s, tk.truncrank(chi), tk.maxiter(nsteps), verbosity=0)
+    s = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=False)
+    out["single"] = tk.run(s, tk.truncrank(chi), tk.maxiter(nsteps), verbosity=0)
     # the opt-in INT8 engine inside the sharded step (chi = 8: 512^3 chunk contractions)
     ref8 = tk.run(tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial)), tk.truncrank(8), tk.maxiter(2),
                   verbosity=0)
@@ -94,6 +99,9 @@ def test_hotrg3d_sharded_two_gpus():
         assert res[r]["ozaki_used"] > 0 and res[r]["ozaki_maxrel"] <= 1e-11
         # the two exchange mechanisms move the same numbers: bit-identical norm lists
         assert res[r]["peers"] == res[r]["nccl"]
+        # projector halves computed on different ranks and broadcast == computed everywhere
+        # == the single-GPU run, bit for bit
+        assert res[r]["peers"] == res[r]["replicated_projectors"] == res[r]["single"]
     assert res[0]["nccl"] == res[1]["nccl"]  # replicas stay bit-identical
     print("peer-scatter launches per rank:", res[0]["peers_peer_launches"],
           "(0 means symmetric memory was unavailable and the NCCL path was used)")

@@ -249,3 +249,60 @@ def test_jacobi_variants_agree(tk, ctx, opt):
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-11 * sref[0]
     assert abs(res[0][2] - res[1][2]) <= 1e-12 * sref[0]
     assert np.abs(res[0][3] - res[1][3]).max() <= 1e-12 * np.abs(res[0][3]).max()
+
+
+def _counter(ctx, name):
+    v = C.c_double()
+    ctx.call("tnr_get_counter", name.encode(), C.byref(v))
+    return v.value
+
+
+@pytest.mark.parametrize("ta,tb", [("T", "N"), ("N", "N"), ("T", "T")])
+def test_gemm_grouped_all_layouts_and_tma_path(tk, ctx, ta, tb):
+    """`tnr_gemm_grouped`: per-sector products in one launch.  With both operands K-contiguous
+    ("T", "N") and >= 148 tiles the launch runs on the TMA + mbarrier kernel with one pair of
+    tensor maps per sector in a device-side table (counter `tma_grouped_launches`); ragged m, n, k
+    are zero-filled by the maps.  Other layouts and small launches use the cp.async kernel."""
+    from tnrkit.jl_b200 import _lib
+
+    rng = np.random.default_rng(42)
+    shapes = [(1500, 1300, 700), (1024, 1024, 1024), (130, 2000, 66), (777, 129, 4100), (8, 8, 64)]
+    keep, probs, refs = [], [], []
+    for m, n, k in shapes:
+        A = rng.standard_normal((k, m) if ta == "T" else (m, k))
+        B = rng.standard_normal((n, k) if tb == "T" else (k, n))
+        C0 = rng.standard_normal((m, n))
+        dA, dB, dC = _up(tk, A), _up(tk, B), _up(tk, C0)
+        keep.append((dA, dB, dC))
+        probs.append(_lib.GemmProblem(m, n, k, dA.buf.data_ptr(), A.shape[0], dB.buf.data_ptr(),
+                                      B.shape[0], dC.buf.data_ptr(), m))
+        refs.append(-0.5 * (A.T if ta == "T" else A) @ (B.T if tb == "T" else B) + 2.0 * C0)
+    arr = (_lib.GemmProblem * len(probs))(*probs)
+    t0, g0 = _counter(ctx, "tma_grouped_launches"), _counter(ctx, "grouped_gemm_launches")
+    ctx.call("tnr_gemm_grouped", ta.encode(), tb.encode(), len(probs), arr, -0.5, 2.0)
+    assert _counter(ctx, "grouped_gemm_launches") == g0 + 1
+    assert _counter(ctx, "tma_grouped_launches") == t0 + (1 if (ta, tb) == ("T", "N") else 0)
+    for (dA, dB, dC), ref, (m, n, k) in zip(keep, refs, shapes):
+        got = dC.to_numpy()
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(k), (m, n, k)
+
+
+def test_gemm_grouped_tma_declines_small_or_unaligned(tk, ctx):
+    from tnrkit.jl_b200 import _lib
+
+    rng = np.random.default_rng(43)
+    for shapes, odd_ld in [([(100, 90, 80), (64, 64, 64)], False), ([(1500, 1300, 701)] * 2, True)]:
+        keep, probs, refs = [], [], []
+        for m, n, k in shapes:
+            A, B = rng.standard_normal((k, m)), rng.standard_normal((k, n))
+            dA, dB, dC = _up(tk, A), _up(tk, B), tk.DeviceTensor.empty((m, n))
+            keep.append((dA, dB, dC))
+            probs.append(_lib.GemmProblem(m, n, k, dA.buf.data_ptr(), k, dB.buf.data_ptr(), k,
+                                          dC.buf.data_ptr(), m))
+            refs.append(A.T @ B)
+        arr = (_lib.GemmProblem * len(probs))(*probs)
+        t0 = _counter(ctx, "tma_grouped_launches")
+        ctx.call("tnr_gemm_grouped", b"T", b"N", len(probs), arr, 1.0, 0.0)
+        assert _counter(ctx, "tma_grouped_launches") == t0      # too few tiles / odd leading dim
+        for (dA, dB, dC), ref in zip(keep, refs):
+            assert np.abs(dC.to_numpy() - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())

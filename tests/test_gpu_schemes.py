@@ -132,3 +132,22 @@ def test_trg_chi32_uses_subspace_svd_and_matches_oracle(tk):
     ctx.call("tnr_get_counter", b"subspace_svd", C.byref(v1))
     assert v1.value > v0.value, "subspace SVD path was never taken"
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
+
+
+def test_hotrg3d_split_entries_and_windowed_d_loop_are_bit_identical(tk, ctx):
+    """`tnr_hotrg3d_proj_half` x 4 + `tnr_hotrg3d_contract` (what a sharded run calls) and the
+    d loop blocked into windows of absorbed operands (`hotrg3d_pk_budget_mb`, the O(chi^7)
+    memory cap) reproduce `tnr_hotrg3d_substep` bit for bit."""
+    T = tk.classical_ising_3D(tk.Trivial)
+    base = tk.run(tk.HOTRG_3D(T, shard=False), tk.truncrank(6), tk.maxiter(4), verbosity=0)
+    forced = tk.run(tk.HOTRG_3D(T, shard=False, split_projectors="force"), tk.truncrank(6),
+                    tk.maxiter(4), verbosity=0)
+    assert forced == base
+    ctx.set_option("hotrg3d_pk_budget_mb", 1)      # 6^6 doubles = 0.37 MB per operand: 2 per window
+    try:
+        windowed = tk.run(tk.HOTRG_3D(T, shard=False), tk.truncrank(6), tk.maxiter(4), verbosity=0)
+    finally:
+        ctx.set_option("hotrg3d_pk_budget_mb", 49152)
+    assert windowed == base
+    ref = np.array(o.run(o.HOTRG_3D(np.asarray(T)), 6, 4))
+    assert np.max(np.abs(np.array(base) - ref) / np.abs(ref)) <= 1e-10

@@ -82,6 +82,9 @@ _SIGNATURES = {
                             C.c_int64],
     "tnr_hotrg3d_substep_peers": [C.c_void_p, _c_dp, _c_i64p, C.c_int, C.POINTER(C.c_void_p),
                                   C.c_int, C.c_int, _c_i64p, C.c_int64, C.c_int64],
+    "tnr_hotrg3d_proj_half": [C.c_void_p, _c_dp, _c_i64p, C.c_int, C.c_int, _c_dp],
+    "tnr_hotrg3d_contract": [C.c_void_p, _c_dp, _c_i64p, C.c_int, _c_dp, C.POINTER(C.c_void_p),
+                             C.c_int, C.c_int, _c_i64p, C.c_int64, C.c_int64],
     "tnr_atrg3d_step": [C.c_void_p, _c_dp, _c_i64p, C.c_int, _c_dp, _c_i64p],
     "tnr_finalize_2d": [C.c_void_p, _c_dp, _c_i64p, C.POINTER(C.c_double)],
     "tnr_finalize_btrg": [C.c_void_p, _c_dp, _c_i64p, _c_dp, _c_dp, C.POINTER(C.c_double)],

@@ -155,6 +155,18 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             ctx->c.permute_unroll = (int)value;
         }
         else if (std::strcmp(key, "permute_bulk") == 0) ctx->c.permute_bulk = value != 0;
+        else if (std::strcmp(key, "hotrg3d_pk_budget_mb") == 0) {
+            TNR_CHECK(value >= 1, "hotrg3d_pk_budget_mb: megabytes of absorbed operands held at once");
+            ctx->c.hotrg3d_pk_budget = (long long)value << 20;
+        }
+        else if (std::strcmp(key, "permute_tpc") == 0) {
+            TNR_CHECK(value >= 1 && value <= 8, "permute_tpc: 1..8");
+            ctx->c.permute_tpc = (int)value;
+        }
+        else if (std::strcmp(key, "permute_chunk_below") == 0) {
+            TNR_CHECK(value >= 0 && value <= 65536, "permute_chunk_below: bytes, 0..65536");
+            ctx->c.permute_chunk_below = (int)value;
+        }
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
@@ -171,6 +183,11 @@ int tnr_gemm_timing(tnr_context* ctx, int enable) {
             cudaEventDestroy(ev.second);
         }
         ctx->c.gemm_events.clear();
+        for (auto& ev : ctx->c.phase_events) {
+            cudaEventDestroy(ev.e0);
+            cudaEventDestroy(ev.e1);
+        }
+        ctx->c.phase_events.clear();
         ctx->c.timed_flops = 0.0;
         ctx->c.time_gemm = enable != 0;
     });
@@ -491,6 +508,50 @@ int tnr_hotrg3d_substep_peers(tnr_context* ctx, const double* T, const int64_t* 
     });
 }
 
+int tnr_hotrg3d_proj_half(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                          int which, double* out) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        Context* c = &ctx->c;
+        TNR_CHECK(out && which >= 0 && which < 4, "proj_half: bad arguments");
+        DT t = in_view(c, T, to_dims(dims, 6));
+        PhaseScope ph(c, "hotrg3d.projectors");
+        Trunc h = hotrg3d_proj_half(c, t, which, chi);
+        const long long nk = h.U.size();
+        TNR_CUDA(cudaMemcpyAsync(out, h.U.p, nk * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        TNR_CUDA(cudaMemcpyAsync(out + nk, h.eps.p, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    });
+}
+
+int tnr_hotrg3d_contract(tnr_context* ctx, const double* T, const int64_t* dims, int chi,
+                         const double* halves, double* const* Tout_peers, int npeers, int self,
+                         int64_t* dims_out, int64_t f_begin, int64_t f_end) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        Context* c = &ctx->c;
+        TNR_CHECK(halves && Tout_peers && npeers >= 1 && npeers <= 16 && self >= 0 && self < npeers,
+                  "hotrg3d_contract: bad arguments");
+        DT t = in_view(c, T, to_dims(dims, 6));
+        Dims od = hotrg3d_substep_dims(t.d, chi);
+        TNR_CHECK(0 <= f_begin && f_begin <= f_end && f_end <= od[5], "contract: bad slice range");
+        const long long Dy = t.d[2], Dx = t.d[3], ny = od[2], nx = od[3];
+        const long long sx = Dx * Dx * nx + 1, sy = Dy * Dy * ny + 1;
+        const double* hx0 = halves;
+        const double* hx1 = halves + sx;
+        const double* hy0 = halves + 2 * sx;
+        const double* hy1 = halves + 2 * sx + sy;
+        DT Ux = hotrg3d_pick(c, DT::view(c, const_cast<double*>(hx0), {Dx, Dx, nx}), hx0 + sx - 1,
+                             DT::view(c, const_cast<double*>(hx1), {Dx, Dx, nx}), hx1 + sx - 1);
+        DT Uy = hotrg3d_pick(c, DT::view(c, const_cast<double*>(hy0), {Dy, Dy, ny}), hy0 + sy - 1,
+                             DT::view(c, const_cast<double*>(hy1), {Dy, Dy, ny}), hy1 + sy - 1);
+        DT out = DT::view(c, Tout_peers[self], od);
+        hotrg3d_contract(c, t, Ux, Uy, out, f_begin, f_end, npeers > 1 ? Tout_peers : nullptr,
+                         npeers > 1 ? npeers : 0);
+        if (dims_out)
+            for (int i = 0; i < 6; ++i) dims_out[i] = od[i];
+    });
+}
+
 int tnr_atrg3d_step(tnr_context* ctx, const double* T, const int64_t* dims, int chi, double* Tout,
                     int64_t* dims_out) {
     if (!ctx) return 1;
@@ -616,10 +677,25 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
     return guard(ctx, [&] {
         const Counters& c = ctx->c.ctr;
         std::string n(name);
+        if (n.rfind("phase_ms.", 0) == 0) {
+            // summed CUDA-event milliseconds of a named phase since tnr_gemm_timing(1)
+            TNR_CUDA(cudaStreamSynchronize(ctx->c.stream));
+            const std::string want = n.substr(9);
+            double ms = 0.0;
+            for (auto& ev : ctx->c.phase_events) {
+                if (want != ev.name) continue;
+                float t = 0.f;
+                TNR_CUDA(cudaEventElapsedTime(&t, ev.e0, ev.e1));
+                ms += t;
+            }
+            *value = ms;
+            return;
+        }
         if (n == "launches") *value = (double)c.launches;
         else if (n == "gemm_launches") *value = (double)c.gemm_launches;
         else if (n == "grouped_gemm_launches") *value = (double)c.grouped_gemm_launches;
         else if (n == "tma_gemm_launches") *value = (double)c.tma_gemm_launches;
+        else if (n == "tma_grouped_launches") *value = (double)c.tma_grouped_launches;
         else if (n == "ozaki_launches") *value = (double)c.ozaki_launches;
         else if (n == "ozaki_gemms") *value = (double)c.ozaki_gemms;
         else if (n == "peer_scatter_launches") *value = (double)c.peer_scatter_launches;

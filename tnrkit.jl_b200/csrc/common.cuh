@@ -37,6 +37,7 @@ struct Counters {
     unsigned long long tma_gemm_launches = 0;  // of which TMA/mbarrier warp-specialised
     unsigned long long ozaki_launches = 0;   // INT8 tcgen05 group kernels
     unsigned long long ozaki_gemms = 0;      // FP64-equivalent GEMMs served by the Ozaki engine
+    unsigned long long tma_grouped_launches = 0;   // grouped (per-sector) launches of the TMA GEMM
     unsigned long long peer_scatter_launches = 0;  // slab scatters that also stored to peer GPUs
     unsigned long long permute_bulk_launches = 0;  // strided copies served by the TMA-fed kernel
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
@@ -60,15 +61,42 @@ struct Context {
     bool disable_block_jacobi = false;  // force the one-pair-per-CTA Jacobi rounds
     int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
     int permute_unroll = 4;  // 1 | 2 | 4: rows of the read phase in flight per thread in the fallback tiled kernel (r02: 4 measured 1.7x faster than 1)
+    int permute_tpc = 8;       // max tiles per CTA of the TMA-fed copy (tuning)
+    int permute_chunk_below = 512;  // rows below this many bytes: cp.async chunks instead of bulk pieces (tuning)
     bool permute_bulk = true;  // TMA-fed tiled copy (cp.async.bulk) whenever the source pieces are 16-byte aligned
     int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    // optional per-phase timing of the scheme bodies (same switch as time_gemm): name + events
+    struct PhaseEvt { const char* name; cudaEvent_t e0, e1; };
+    std::vector<PhaseEvt> phase_events;
+    long long hotrg3d_pk_budget = 48LL << 30;  // bytes of absorbed operands Pk_d held at once
     std::string last_error;
     // multi-GPU sharding of the HOTRG_3D open bond (set by tnr_set_shard)
     int rank = 0, world = 1;
+};
+
+// Times a phase of a scheme body with CUDA events on ctx->stream while gemm timing is on
+// (bench.py); free otherwise.  Read back with tnr_get_counter("phase_ms.<name>").
+struct PhaseScope {
+    Context* ctx;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const char* name;
+    PhaseScope(Context* c, const char* nm) : ctx(c), name(nm) {
+        if (!ctx->time_gemm) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    void stop() {
+        if (!e0 || !e1) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->phase_events.push_back({name, e0, e1});
+        e0 = e1 = nullptr;
+    }
+    ~PhaseScope() { stop(); }
 };
 
 // ---- device memory (stream ordered) ----
@@ -99,11 +127,14 @@ struct GroupedProblem {
 };
 void gemm_grouped(Context* ctx, char transa, char transb, const std::vector<GroupedProblem>& probs,
                   double alpha, double beta);
+bool gemm_grouped_tma_tn(Context* ctx, const std::vector<GroupedProblem>& probs, double alpha,
+                         double beta);
 
 // gemm_tma.cu: warp-specialised TMA + mbarrier + DMMA kernel for the TN layout; returns false
 // when the problem does not fit (caller falls back to the cp.async kernel)
 bool gemm_tma_tn(Context* ctx, int m, int n, int k, double alpha, const double* A, long long lda,
                  const double* B, long long ldb, double beta, double* C, long long ldc);
+// grouped TN products (per-sector blocks) on the same kernel, one launch; false = not applicable
 
 // gemm_ozaki.cu: FP64-accurate TN GEMM on the INT8 tensor cores (tcgen05 + TMEM), opt-in
 struct OzakiOperand {        // int8 digit planes of the rows of a K-major FP64 matrix

@@ -478,6 +478,8 @@ void launch_grouped_layout(Context* ctx, std::vector<GemmParams>& tab, bool narr
 void gemm_grouped(Context* ctx, char transa, char transb, const std::vector<GroupedProblem>& probs,
                   double alpha, double beta) {
     bool ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+    // both operands K-contiguous: the TMA + mbarrier kernel, when every sector fits it
+    if (ta && !tb && gemm_grouped_tma_tn(ctx, probs, alpha, beta)) return;
     std::vector<GemmParams> tab;
     bool narrow = true;
     auto even = [](long long x) { return (x & 1LL) == 0; };

@@ -81,9 +81,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // distinct 8-byte banks.
 __device__ __forceinline__ int rho(int q) { return 2 * (q & 3) + (q >> 2); }
 
-__global__ void __launch_bounds__(TMA_THREADS, 1)
-gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
-                     const __grid_constant__ CUtensorMap mapB, const TmaParams p) {
+// One 128 x 128 output tile: `t` is the tile index inside the problem described by p / mapA / mapB.
+__device__ __forceinline__ void tma_tile(const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                         const TmaParams& p, int t) {
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned stage ring (128B swizzle atom = 8 rows x 128 B)
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -91,7 +91,6 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + TSTAGES);
 
     const int GROUP = 8;
-    int t = blockIdx.x;
     int per_group = GROUP * p.tiles_n;
     int group_id = t / per_group;
     int first_m = group_id * GROUP;
@@ -115,8 +114,8 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
     if (warp == CONSUMER_WARPS) {
         // ===================== producer warp =====================
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA));
-            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB));
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA));
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB));
             for (int kt = 0; kt < KT; ++kt) {
                 int s = kt % TSTAGES;
                 int ph = (kt / TSTAGES) & 1;
@@ -124,8 +123,8 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
                 unsigned full = full0 + 8 * s;
                 mbar_arrive_expect_tx(full, STAGE_BYTES);
                 unsigned dstA = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                tma_load_2d(dstA, &mapA, kt * TBK, m0, full);
-                tma_load_2d(dstA + A_BYTES, &mapB, kt * TBK, n0, full);
+                tma_load_2d(dstA, mapA, kt * TBK, m0, full);
+                tma_load_2d(dstA + A_BYTES, mapB, kt * TBK, n0, full);
             }
         }
         // the producer warp idles until the consumers are done (no smem reuse hazards: the
@@ -211,6 +210,35 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
     }
 }
 
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA,
+                     const __grid_constant__ CUtensorMap mapB, const TmaParams p) {
+    tma_tile(&mapA, &mapB, p, blockIdx.x);
+}
+
+// Grouped launch: the per-sector products of a block-sparse contraction (TensorKit `mul!` over
+// `blocks(t)`: src/schemes/trg.jl:42, btrg.jl:86-94 on Z2 / ZN / U1 tensors) in ONE launch of
+// the same TMA + mbarrier + DMMA tile.  Every problem has its own pair of tensor maps in a
+// device-side table; a CTA finds its problem from the prefix sums of the tile counts.
+struct alignas(64) GroupedTmaEntry {
+    CUtensorMap mapA, mapB;   // 128 bytes each, 64-byte aligned
+    TmaParams p;
+    int tile_start;           // first global tile index of this problem
+    int pad_;
+};
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gemm_dmma_tma_grouped_kernel(const GroupedTmaEntry* __restrict__ table, int count) {
+    const int t = blockIdx.x;
+    int lo = 0, hi = count - 1;             // last entry with tile_start <= t
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].tile_start <= t) lo = mid; else hi = mid - 1;
+    }
+    const GroupedTmaEntry* e = table + lo;
+    tma_tile(&e->mapA, &e->mapB, e->p, t - e->tile_start);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -274,6 +302,59 @@ bool gemm_tma_tn(Context* ctx, int m, int n, int k, double alpha, const double* 
     ctx->ctr.launches++;
     ctx->ctr.gemm_launches++;
     ctx->ctr.tma_gemm_launches++;
+    return true;
+}
+
+// Grouped TN products on the TMA kernel.  Returns false (nothing launched) unless EVERY problem
+// fits the TMA path (16-byte aligned K-contiguous operands) and the launch fills the GPU; the
+// caller then uses the cp.async grouped kernel.
+bool gemm_grouped_tma_tn(Context* ctx, const std::vector<GroupedProblem>& probs, double alpha,
+                         double beta) {
+    if (ctx->disable_tma || probs.empty()) return false;
+    std::vector<GroupedTmaEntry> tab;
+    tab.reserve(probs.size());
+    long long tiles = 0;
+    for (const GroupedProblem& q : probs) {
+        if (q.m <= 0 || q.n <= 0) continue;
+        if (((uintptr_t)q.A & 15) || ((uintptr_t)q.B & 15) || (q.lda & 1) || (q.ldb & 1)) return false;
+        if (q.lda * 8 >= (1LL << 40) || q.ldb * 8 >= (1LL << 40)) return false;
+        if (q.k < 4 * TBK) return false;
+        GroupedTmaEntry e{};
+        if (!make_map(&e.mapA, q.A, q.m, q.k, q.lda, TBM) || !make_map(&e.mapB, q.B, q.n, q.k, q.ldb, TBN))
+            return false;
+        e.p.C = q.C; e.p.ldc = q.ldc; e.p.M = q.m; e.p.N = q.n; e.p.K = q.k;
+        e.p.alpha = alpha; e.p.beta = beta;
+        e.p.tiles_m = (q.m + TBM - 1) / TBM; e.p.tiles_n = (q.n + TBN - 1) / TBN;
+        e.p.c16 = ((uintptr_t)q.C % 16 == 0) && ((q.ldc & 1) == 0);
+        e.tile_start = (int)tiles;
+        tiles += (long long)e.p.tiles_m * e.p.tiles_n;
+        tab.push_back(e);
+    }
+    // small launches: the cp.async kernel has split-K and narrow tiles; this one has neither
+    if (tab.empty() || tiles < ctx->num_sms || tiles >= (1LL << 31)) return false;
+    static bool configured = false;
+    if (!configured) {
+        TNR_CUDA(cudaFuncSetAttribute(gemm_dmma_tma_grouped_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        configured = true;
+    }
+    const size_t bytes = tab.size() * sizeof(GroupedTmaEntry);
+    GroupedTmaEntry* dtab = nullptr;
+    TNR_CUDA(cudaMallocAsync((void**)&dtab, bytes, ctx->stream));
+    TNR_CHECK(((uintptr_t)dtab & 63) == 0, "grouped TMA table: allocation is not 64-byte aligned");
+    // pageable source: the runtime stages the bytes before returning, `tab` may go out of scope
+    TNR_CUDA(cudaMemcpyAsync(dtab, tab.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    gemm_dmma_tma_grouped_kernel<<<(unsigned)tiles, TMA_THREADS, TMA_SMEM, ctx->stream>>>(
+        dtab, (int)tab.size());
+    TNR_CUDA(cudaGetLastError());
+    TNR_CUDA(cudaFreeAsync(dtab, ctx->stream));
+    for (const GroupedProblem& q : probs)
+        if (q.m > 0 && q.n > 0) ctx->ctr.gemm_flops += 2.0 * q.m * q.n * (double)q.k;
+    ctx->ctr.launches++;
+    ctx->ctr.gemm_launches++;
+    ctx->ctr.grouped_gemm_launches++;
+    ctx->ctr.tma_gemm_launches++;
+    ctx->ctr.tma_grouped_launches++;
     return true;
 }
 

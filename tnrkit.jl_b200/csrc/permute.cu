@@ -125,34 +125,80 @@ struct Store2 {
     }
 };
 
+struct Issue16 {
+    __device__ __forceinline__ void operator()(double* tp, const double* sp) const {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                     ::"r"(bsmem_u32(tp)), "l"(sp) : "memory");
+    }
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict__ src,
                                                         double* __restrict__ dst,
                                                         const BulkParams p) {
     extern __shared__ __align__(16) double tile[];
-    __shared__ unsigned long long bar_storage;
-    const unsigned bar = bsmem_u32(&bar_storage);
-    const BulkGeom g = bulk_geometry(src, dst, p, blockIdx.x);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-                     ::"r"(bar), "r"((int)bulk_tile_bytes(g)) : "memory");
+    __shared__ unsigned long long bar_storage[BULK_MAX_TPC];
+    __shared__ BulkGeom sgeom[BULK_MAX_TPC];
+    const long long t0 = (long long)blockIdx.x * p.tpc;
+    const int nt = (int)min((long long)p.tpc, p.ntiles - t0);
+    const long long tile_elems = bulk_tile_elems(p);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile origins (64-bit divisions) once per CTA, by the first nt lanes of warp 0
+    if (warp == 0) {
+        if (lane < nt) sgeom[lane] = bulk_geometry(src, dst, p, t0 + lane);
+        if (lane == 0 && !p.chunked) {
+            for (int t = 0; t < nt; ++t)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n"
+                             ::"r"(bsmem_u32(&bar_storage[t])), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
     }
     __syncthreads();
-    bulk_load_phase(g, p, tile, threadIdx.x, 256, BulkIssue{bar});
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "BWAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra BDONE;\n"
-        "bra BWAIT;\n"
-        "BDONE:\n"
-        "}\n" ::"r"(bar), "r"(0) : "memory");
-    if (VEC == 2) bulk_write_phase<2>(g, p, tile, threadIdx.x, Store2{});
-    else bulk_write_phase<1>(g, p, tile, threadIdx.x, Store1{});
+    for (int t = 0; t < nt; ++t) {
+        const BulkGeom g = sgeom[t];
+        if (!p.chunked) {
+            const unsigned bar = bsmem_u32(&bar_storage[t]);
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                             ::"r"(bar), "r"((int)bulk_tile_bytes(g)) : "memory");
+            bulk_load_phase(g, p, tile + t * tile_elems, threadIdx.x, 256, BulkIssue{bar});
+        } else {
+            bulk_load_phase_chunked(g, p, tile + t * tile_elems, threadIdx.x, 256, Issue16{});
+        }
+    }
+    // the write-phase slots of a full tile, computed while the loads are in flight
+    BulkLaneTab full_tab;
+    bulk_lane_table(p, p.TV, p.TJ1, p.TJ1 * p.TJ2, lane, VEC, full_tab);
+    if (p.chunked) {
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+    }
+    for (int t = 0; t < nt; ++t) {
+        if (!p.chunked) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "BWAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra BDONE;\n"
+                "bra BWAIT;\n"
+                "BDONE:\n"
+                "}\n" ::"r"(bsmem_u32(&bar_storage[t])), "r"(0) : "memory");
+        }
+        const BulkGeom g = sgeom[t];
+        const bool full = g.tv == p.TV && g.tj1 == p.TJ1 && g.cj == p.TJ1 * p.TJ2;
+        if (full) {
+            if (VEC == 2) bulk_write_phase<2>(g, p, tile + t * tile_elems, warp, full_tab, Store2{});
+            else bulk_write_phase<1>(g, p, tile + t * tile_elems, warp, full_tab, Store1{});
+        } else {                                  // ragged tile (rare): its own slots
+            BulkLaneTab tab;
+            bulk_lane_table(p, g.tv, g.tj1, g.cj, lane, VEC, tab);
+            if (VEC == 2) bulk_write_phase<2>(g, p, tile + t * tile_elems, warp, tab, Store2{});
+            else bulk_write_phase<1>(g, p, tile + t * tile_elems, warp, tab, Store1{});
+        }
+    }
 }
 
 // same fastest index on both sides: one thread per element, inner index fastest.  T = double2
@@ -238,8 +284,11 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
     CopyParams& p = plan.p;
     if (plan.kind != COPY_FLAT && ctx->permute_bulk) {
         // the TMA-fed kernel whenever the copy has 16-byte aligned source pieces
+        BulkTuning tune;
+        tune.max_tpc = ctx->permute_tpc;
+        tune.chunk_below = ctx->permute_chunk_below;
         BulkPlan bp = plan_bulk_copy(merged_groups(rank, dims, sstride, dstride), (uintptr_t)src,
-                                     (uintptr_t)dst, ctx->permute_tile);
+                                     (uintptr_t)dst, ctx->permute_tile, tune);
         if (bp.ok) {
             static bool bulk_configured = false;
             if (!bulk_configured) {

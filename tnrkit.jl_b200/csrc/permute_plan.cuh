@@ -197,6 +197,7 @@ inline std::vector<BulkGroup> merged_groups(int rank, const long long* dims,
 // =====================================================================================
 constexpr int BULK_KMAX = 6;          // elements (of VEC doubles) per lane and output run
 constexpr int BULK_TILE_ELEMS = 9216; // doubles per tile (72 KB): 3 CTAs per SM
+constexpr int BULK_MAX_TPC = 8;       // tiles per CTA
 
 struct BulkParams {
     int rank;
@@ -210,6 +211,9 @@ struct BulkParams {
     int contig1, contig2;   // source row of a tile: (v,i1) contiguous / (v,i1,i2) contiguous
     int vec;                // 2: 16-byte shared loads + global stores in the write phase, else 1
     int R;                  // i1 rows written per warp pass (short destination runs are batched)
+    int tpc;                // tiles per CTA (small tiles: several in flight per CTA)
+    int chunked;            // 1: rows shorter than 512 B are fetched as 16-byte cp.async chunks
+    long long ntiles;       // total number of tiles (grid = ceil(ntiles / tpc))
 };
 
 struct BulkPlan {
@@ -230,8 +234,14 @@ inline int bulk_pick_extent(long long n, long long tgt, bool want_even) {
 
 // m: merged groups in destination order (m[0] destination-fastest).  Returns ok = false when
 // the copy does not have the structure / alignment the bulk kernel needs.
+struct BulkTuning {
+    int max_tpc = BULK_MAX_TPC;     // tiles per CTA (1 = one tile per CTA)
+    int chunk_below = 512;          // whole-row pieces below this many bytes use cp.async chunks
+};
+
 inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_addr,
-                               uintptr_t dst_addr, int tile_tgt) {
+                               uintptr_t dst_addr, int tile_tgt,
+                               const BulkTuning& tune = BulkTuning()) {
     BulkPlan out;
     const size_t none = (size_t)-1;
     if (m.empty() || m.size() > (size_t)MAXR + 4) return out;
@@ -269,6 +279,8 @@ inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_ad
     G(j1, p.n_j1, p.s_j1, p.d_j1); G(j2, p.n_j2, p.s_j2, p.d_j2);
     p.rank = 0;
     long long outer = 1;
+    for (size_t i = 0; i < m.size(); ++i)
+        if (m[i].n >= (1LL << 31)) return out;       // 32-bit index arithmetic in the kernel
     for (size_t i = 0; i < m.size(); ++i) {
         if (used[i]) continue;
         if (p.rank >= MAXR) return out;
@@ -342,10 +354,23 @@ inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_ad
     if ((pitch / 2) % 2 == 0) pitch += 2;
     if (pitch > (1 << 20)) return out;
     p.pitch = (int)pitch;
-    out.smem = (size_t)p.TJ1 * p.TJ2 * pitch * sizeof(double);
-    if (out.smem > 100 * 1024) return out;
-    out.blocks = p.tiles_v * p.tiles_i1 * p.tiles_i2 * p.tiles_j1 * p.tiles_j2 * outer;
-    if (out.blocks >= (1LL << 31) || out.blocks <= 0) return out;
+    const size_t tile_smem = (size_t)p.TJ1 * p.TJ2 * pitch * sizeof(double);
+    if (tile_smem > 100 * 1024) return out;
+    p.ntiles = p.tiles_v * p.tiles_i1 * p.tiles_i2 * p.tiles_j1 * p.tiles_j2 * outer;
+    if (p.ntiles >= (1LL << 31) || p.ntiles <= 0) return out;
+    // small tiles: several per CTA, all requested up front (about 72 KB per CTA either way)
+    long long tpc = (long long)(BULK_TILE_ELEMS * sizeof(double)) / (long long)tile_smem;
+    if (tpc < 1) tpc = 1;
+    if (tpc > BULK_MAX_TPC) tpc = BULK_MAX_TPC;
+    if (tpc > tune.max_tpc) tpc = std::max(1, tune.max_tpc);
+    // keep at least ~4 CTAs per SM worth of blocks
+    while (tpc > 1 && p.ntiles / tpc < 148 * 4) --tpc;
+    p.tpc = (int)tpc;
+    // whole-row pieces below 512 bytes go through 16-byte cp.async chunks instead of one bulk
+    // request per piece
+    p.chunked = (p.contig2 && row * 8 < tune.chunk_below) ? 1 : 0;
+    out.smem = tile_smem * (size_t)tpc;
+    out.blocks = (p.ntiles + tpc - 1) / tpc;
     out.ok = true;
     return out;
 }
@@ -356,24 +381,29 @@ struct BulkGeom {
     int tv, ti1, ti2, tj1, tj2, ci, cj;
 };
 
-TNR_HD BulkGeom bulk_geometry(const double* src, double* dst, const BulkParams& p, long long bid) {
-    long long t_v = bid % p.tiles_v; bid /= p.tiles_v;
-    long long t_i1 = bid % p.tiles_i1; bid /= p.tiles_i1;
-    long long t_i2 = bid % p.tiles_i2; bid /= p.tiles_i2;
-    long long t_j1 = bid % p.tiles_j1; bid /= p.tiles_j1;
-    long long t_j2 = bid % p.tiles_j2; bid /= p.tiles_j2;
+TNR_HD BulkGeom bulk_geometry(const double* src, double* dst, const BulkParams& p, long long bid64) {
+    // the planner guarantees ntiles < 2^31 and every extent < 2^31: 32-bit divisions
+    unsigned bid = (unsigned)bid64;
+    unsigned q;
+    q = bid / (unsigned)p.tiles_v;  const unsigned t_v = bid - q * (unsigned)p.tiles_v;   bid = q;
+    q = bid / (unsigned)p.tiles_i1; const unsigned t_i1 = bid - q * (unsigned)p.tiles_i1; bid = q;
+    q = bid / (unsigned)p.tiles_i2; const unsigned t_i2 = bid - q * (unsigned)p.tiles_i2; bid = q;
+    q = bid / (unsigned)p.tiles_j1; const unsigned t_j1 = bid - q * (unsigned)p.tiles_j1; bid = q;
+    q = bid / (unsigned)p.tiles_j2; const unsigned t_j2 = bid - q * (unsigned)p.tiles_j2; bid = q;
     long long soff = 0, doff = 0;
 #pragma unroll
     for (int d = 0; d < MAXR; ++d) {
         if (d < p.rank) {
-            long long i = bid % p.dims[d];
-            bid /= p.dims[d];
+            q = bid / (unsigned)p.dims[d];
+            const long long i = bid - q * (unsigned)p.dims[d];
+            bid = q;
             soff += i * p.ss[d];
             doff += i * p.ds[d];
         }
     }
-    const long long v0 = t_v * p.TV, i10 = t_i1 * p.TI1, i20 = t_i2 * p.TI2, j10 = t_j1 * p.TJ1,
-                    j20 = t_j2 * p.TJ2;
+    const long long v0 = (long long)t_v * p.TV, i10 = (long long)t_i1 * p.TI1,
+                    i20 = (long long)t_i2 * p.TI2, j10 = (long long)t_j1 * p.TJ1,
+                    j20 = (long long)t_j2 * p.TJ2;
     BulkGeom g;
     g.tv = (int)((p.n_v - v0 < p.TV) ? p.n_v - v0 : p.TV);
     g.ti1 = (int)((p.n_i1 - i10 < p.TI1) ? p.n_i1 - i10 : p.TI1);
@@ -391,61 +421,105 @@ TNR_HD long long bulk_tile_bytes(const BulkGeom& g) {
     return (long long)g.cj * g.ci * g.tv * 8;
 }
 
+TNR_HD long long bulk_tile_elems(const BulkParams& p) {
+    return (long long)p.TJ1 * p.TJ2 * p.pitch;
+}
+
+// chunked load phase (rows shorter than 512 B, contiguous in the source): every thread fetches
+// 16-byte chunks; `issue16(dst, src)` is cp.async (LDGSTS) on the device
+template <typename Issue16>
+TNR_HD void bulk_load_phase_chunked(const BulkGeom& g, const BulkParams& p, double* tile, int tid,
+                                    int nthreads, Issue16 issue16) {
+    const unsigned cpr = (unsigned)(g.ci * g.tv) / 2;   // 16-byte chunks per row
+    const unsigned total = (unsigned)g.cj * cpr;
+    for (unsigned c = (unsigned)tid; c < total; c += (unsigned)nthreads) {
+        const unsigned r = c / cpr, o = c - r * cpr;
+        const unsigned j2 = (g.cj == g.tj1) ? 0u : r / (unsigned)g.tj1;
+        const unsigned j1 = r - j2 * (unsigned)g.tj1;
+        issue16(tile + (long long)r * p.pitch + 2 * o,
+                g.sp + (long long)j1 * p.s_j1 + (long long)j2 * p.s_j2 + 2 * o);
+    }
+}
+
 // load phase: the pieces of the tile are dealt round-robin to the threads; `issue(dst, src,
 // bytes)` is cp.async.bulk on the device and memcpy in the host check
 template <typename Issue>
 TNR_HD void bulk_load_phase(const BulkGeom& g, const BulkParams& p, double* tile, int tid,
                             int nthreads, Issue issue) {
-    const int np1 = p.contig1 ? 1 : g.ti1;
-    const int np2 = p.contig2 ? 1 : g.ti2;
-    const int np = np1 * np2;
+    const unsigned np1 = p.contig1 ? 1u : (unsigned)g.ti1;
+    const unsigned np2 = p.contig2 ? 1u : (unsigned)g.ti2;
+    const unsigned np = np1 * np2;
     const int plen = g.tv * (p.contig1 ? g.ti1 : 1) * (p.contig2 ? g.ti2 : 1);
-    const int total = g.cj * np;
-    for (int q = tid; q < total; q += nthreads) {
-        const int r = q / np, pc = q - r * np;
-        const int a1 = pc % np1, a2 = pc / np1;
-        const int j1 = r % g.tj1, j2 = r / g.tj1;
-        const double* sp = g.sp + j1 * p.s_j1 + j2 * p.s_j2 + a1 * p.s_i1 + a2 * p.s_i2;
-        double* tp = tile + (long long)r * p.pitch + (a2 * g.ti1 + a1) * g.tv;
+    const unsigned total = (unsigned)g.cj * np;
+    for (unsigned q = (unsigned)tid; q < total; q += (unsigned)nthreads) {
+        unsigned r = q, a1 = 0, a2 = 0;
+        if (np > 1) {
+            r = q / np;
+            const unsigned pc = q - r * np;
+            a2 = (np1 == 1) ? pc : pc / np1;
+            a1 = pc - a2 * np1;
+        }
+        const unsigned j2 = (g.cj == g.tj1) ? 0u : r / (unsigned)g.tj1;
+        const unsigned j1 = r - j2 * (unsigned)g.tj1;
+        const double* sp = g.sp + (long long)j1 * p.s_j1 + (long long)j2 * p.s_j2 +
+                           (long long)a1 * p.s_i1 + (long long)a2 * p.s_i2;
+        double* tp = tile + (long long)r * p.pitch + (int)((a2 * (unsigned)g.ti1 + a1) * (unsigned)g.tv);
         issue(tp, sp, plen * 8);
     }
 }
 
-// write phase: a warp pass writes R consecutive i1 rows of the tile (same i2); the lanes run
-// along (row, destination run (j2, j1, v)) of the pass, VEC doubles per lane and access
-template <int VEC, typename Store>
-TNR_HD void bulk_write_phase(const BulkGeom& g, const BulkParams& p, const double* tile, int tid,
-                             Store store) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int run = g.cj * g.tv;
-    const int R = p.R;
-    int so[BULK_KMAX], ri[BULK_KMAX];
-    long long dof[BULK_KMAX];
+// Per-lane slots of the write phase: a warp pass writes R consecutive i1 rows of the tile (same
+// i2); the lanes run along (row, destination run (j2, j1, v)) of the pass, VEC doubles per lane
+// and slot.  The table depends only on the tile's (tv, tj1, cj), i.e. it is the same for every
+// full tile: the kernel computes it once per CTA (warp 0 -> shared memory) instead of once per
+// thread and tile -- the integer divisions here were the limiter of small tiles.
+struct BulkLaneTab {
+    int so[BULK_KMAX];        // shared-memory offset of the slot (doubles), -1 = unused
+    int ri[BULK_KMAX];        // row of the pass the slot belongs to
+    long long dof[BULK_KMAX]; // destination offset relative to the pass origin
+};
+
+TNR_HD void bulk_lane_table(const BulkParams& p, int tv, int tj1, int cj, int lane, int vec,
+                            BulkLaneTab& T) {
+    const unsigned run = (unsigned)(cj * tv);
+    const unsigned R = (unsigned)p.R;
 #pragma unroll
     for (int k = 0; k < BULK_KMAX; ++k) {
-        const int e = (lane + 32 * k) * VEC;
-        so[k] = -1;
-        ri[k] = 0;
-        dof[k] = 0;
+        const unsigned e = (unsigned)((lane + 32 * k) * vec);
+        T.so[k] = -1;
+        T.ri[k] = 0;
+        T.dof[k] = 0;
         if (e < R * run) {
-            const int rr = e / run, x = e - rr * run;
-            const int jj = x / g.tv, v = x - jj * g.tv;
-            const int j1 = jj % g.tj1, j2 = jj / g.tj1;
-            ri[k] = rr;
-            so[k] = jj * p.pitch + rr * g.tv + v;
-            dof[k] = rr * p.d_i1 + j1 * p.d_j1 + j2 * p.d_j2 + v;
+            const unsigned rr = e / run, x = e - rr * run;
+            const unsigned jj = (tv == 1) ? x : x / (unsigned)tv;
+            const unsigned v = x - jj * (unsigned)tv;
+            const unsigned j2 = (cj == tj1) ? 0u : jj / (unsigned)tj1;
+            const unsigned j1 = jj - j2 * (unsigned)tj1;
+            T.ri[k] = (int)rr;
+            T.so[k] = (int)(jj * (unsigned)p.pitch + rr * (unsigned)tv + v);
+            T.dof[k] = (long long)rr * p.d_i1 + (long long)j1 * p.d_j1 + (long long)j2 * p.d_j2 + v;
         }
     }
+}
+
+template <int VEC, typename Store>
+TNR_HD void bulk_write_phase(const BulkGeom& g, const BulkParams& p, const double* tile, int warp,
+                             const BulkLaneTab& T, Store store) {
+    const int R = p.R;
     const int blocks1 = (g.ti1 + R - 1) / R;          // passes per i2 slice
     const int passes = blocks1 * g.ti2;
+    int i2 = 0, b1 = warp;                            // pass q = i2 * blocks1 + b1
+    while (b1 >= blocks1) { b1 -= blocks1; ++i2; }
     for (int q = warp; q < passes; q += 8) {
-        const int i2 = q / blocks1, i10 = (q - i2 * blocks1) * R;
+        const int i10 = b1 * R;
         const int left = g.ti1 - i10;
         double* gp = g.dp + i10 * p.d_i1 + i2 * p.d_i2;
         const double* t = tile + (i2 * g.ti1 + i10) * g.tv;
 #pragma unroll
         for (int k = 0; k < BULK_KMAX; ++k)
-            if (so[k] >= 0 && ri[k] < left) store(gp + dof[k], t + so[k]);
+            if (T.so[k] >= 0 && T.ri[k] < left) store(gp + T.dof[k], t + T.so[k]);
+        b1 += 8;
+        while (b1 >= blocks1) { b1 -= blocks1; ++i2; }
     }
 }
 

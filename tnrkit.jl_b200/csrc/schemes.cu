@@ -251,6 +251,20 @@ DT hotrg3d_proj(Context* ctx, const DT& A1, const DT& A2, int o_left, int o_righ
 
 }  // namespace
 
+Trunc hotrg3d_proj_half(Context* ctx, const DT& T, int which, int chi) {
+    static const int open_leg[4] = {5, 3, 4, 2};
+    TNR_CHECK(which >= 0 && which < 4, "hotrg3d_proj_half: which in 0..3");
+    return eigh_trunc(hotrg3d_mm(ctx, T, T, open_leg[which]), 2, chi);
+}
+
+DT hotrg3d_pick(Context* ctx, const DT& Ul, const double* eps_l, const DT& Ur,
+                const double* eps_r) {
+    TNR_CHECK(Ul.d == Ur.d, "hotrg3d_pick: projector halves differ in shape");
+    DT U(ctx, Ul.d);
+    select_copy(ctx, U.p, Ul.p, Ur.p, U.size(), eps_l, eps_r, nullptr);
+    return U;
+}
+
 Dims hotrg3d_substep_dims(const Dims& d, int chi) {
     long long nx = std::min<long long>(chi, d[5] * d[5]);
     long long ny = std::min<long long>(chi, d[4] * d[4]);
@@ -266,10 +280,21 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
     TNR_CHECK(Tout.d == od, "hotrg3d: output dims");
     const long long Dz = T.d[0], Dy = T.d[2], Dx = T.d[3];
     const long long ny = od[2], nx = od[3];
+    PhaseScope ph_proj(ctx, "hotrg3d.projectors");
     DT Ux = hotrg3d_proj(ctx, T, T, 5, 3, chi);  // [x1 x2 nx]
     DT Uy = hotrg3d_proj(ctx, T, T, 4, 2, chi);  // [y1 y2 ny]
+    ph_proj.stop();
+    hotrg3d_contract(ctx, T, Ux, Uy, Tout, f0, f1, peers, npeers);
+}
 
-    // hotrg3d.jl:116-120
+// hotrg3d.jl:116-120 with the projectors given, for the slices f0 <= f < f1 of the new x-bond
+void hotrg3d_contract(Context* ctx, const DT& T, const DT& Ux, const DT& Uy, DT& Tout,
+                      long long f0, long long f1, double* const* peers, int npeers) {
+    const Dims& od = Tout.d;
+    const long long Dz = T.d[0], Dy = T.d[2], Dx = T.d[3];
+    const long long ny = od[2], nx = od[3];
+    TNR_CHECK(Ux.d == Dims({Dx, Dx, nx}) && Uy.d == Dims({Dy, Dy, ny}), "hotrg3d: projector dims");
+
     //  T[a b c d e f] = Ux[x1 x2 f] Ux[x1' x2' d] Uy[y1 y2 e] Uy[y1' y2' c]
     //                   A1[a z y1' x1' y1 x1] A2[z b y2' x2' y2 x2]
     // chunked over the open bonds (f, d):  R_fd = Qk_f^T Pk_d  is a (Dz Dy Dy)^2 x (Dz Dx Dx) GEMM
@@ -279,21 +304,53 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
     // opt-in: the chunk GEMM on the INT8 tensor cores (Ozaki scheme, gemm_ozaki.cu); operands
     // are split into digit planes once per d / once per f and reused by all chunks
     const bool oz = ozaki_applicable(ctx, mdim, mdim, kdim);
-    DT A2p = permute(T, {3, 0, 1, 2, 4, 5});  // [X | z b Y y x]
-    std::vector<DT> Pk;
-    std::vector<OzakiOperand> Pk8;
-    Pk.reserve(nx);
-    for (long long d = 0; d < nx; ++d) {
-        DT Uxd = DT::view(ctx, Ux.p + d * Dx * Dx, {Dx, Dx});  // [x1' x2']
-        DT Pn = contract(A2p, "XzbYyx", Uxd, "pX", "zbYyxp");
-        DT Pd = permute(Pn, {0, 5, 4, 3, 1, 2});  // [z p x | y b Y]
-        if (oz) Pk8.push_back(ozaki_split(ctx, Pd.p, kdim, mdim, kdim));
-        else Pk.push_back(std::move(Pd));
+    // The absorbed operands Pk_d (kdim x mdim doubles each, nx of them: O(chi^7) memory) are
+    // built for a WINDOW of d at a time, capped by a byte budget and by the free device memory;
+    // Qk_f is rebuilt per window (one chi^7 contraction against the window's nx_w chi^9 GEMMs).
+    const double pk_bytes = (double)kdim * (double)mdim * 8.0 * (oz ? 2.0 : 1.0);
+    size_t free_b = 0, total_b = 0;
+    TNR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    {   // blocks cached by the stream-ordered pool are reusable as well
+        cudaMemPool_t pool = nullptr;
+        unsigned long long reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess &&
+            reserved > used)
+            free_b += (size_t)(reserved - used);
+        else
+            (void)cudaGetLastError();
     }
-    A2p.release();
+    // working set besides the window: A2p + Pn + Qn + Qk (4 operand-sized) + R, S, W
+    const double reserve = 5.0 * pk_bytes + 3.0 * (double)mdim * (double)mdim * 8.0;
+    double budget = std::min((double)ctx->hotrg3d_pk_budget, 0.9 * (double)free_b - reserve);
+    long long win = (long long)std::floor(budget / pk_bytes);
+    TNR_CHECK(win >= 1,
+              "hotrg3d: not enough device memory for one absorbed operand Pk_d plus the working "
+              "set (" + std::to_string((pk_bytes + reserve) / 1e9) + " GB needed, " +
+                  std::to_string((double)free_b / 1e9) + " GB free)");
+    if (win > nx) win = nx;
     const long long so[6] = {1, od[0], od[0] * od[1], od[0] * od[1] * od[2],
                              od[0] * od[1] * od[2] * od[3], od[0] * od[1] * od[2] * od[3] * od[4]};
+    DT A2p = permute(T, {3, 0, 1, 2, 4, 5});  // [X | z b Y y x]
+    for (long long d0 = 0; d0 < nx; d0 += win) {
+    const long long d1 = std::min(nx, d0 + win);
+    std::vector<DT> Pk;
+    std::vector<OzakiOperand> Pk8;
+    Pk.reserve(d1 - d0);
+    {
+        PhaseScope ph(ctx, "hotrg3d.pk_build");
+        for (long long d = d0; d < d1; ++d) {
+            DT Uxd = DT::view(ctx, Ux.p + d * Dx * Dx, {Dx, Dx});  // [x1' x2']
+            DT Pn = contract(A2p, "XzbYyx", Uxd, "pX", "zbYyxp");
+            DT Pd = permute(Pn, {0, 5, 4, 3, 1, 2});  // [z p x | y b Y]
+            if (oz) Pk8.push_back(ozaki_split(ctx, Pd.p, kdim, mdim, kdim));
+            else Pk.push_back(std::move(Pd));
+        }
+    }
+    if (d1 == nx) A2p.release();
     for (long long f = f0; f < f1; ++f) {
+        PhaseScope ph_q(ctx, "hotrg3d.q_build");
         DT Uxf = DT::view(ctx, Ux.p + f * Dx * Dx, {Dx, Dx});  // [x1 x2]
         DT Qn = contract(T, "azYXyx", Uxf, "xq", "azYXyq");
         DT Qk = permute(Qn, {1, 3, 5, 0, 2, 4});  // [z X q | a Y y]
@@ -303,7 +360,8 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
             Q8 = ozaki_split(ctx, Qk.p, kdim, mdim, kdim);
             Qk.release();
         }
-        for (long long d = 0; d < nx; ++d) {
+        ph_q.stop();
+        for (long long d = d0; d < d1; ++d) {
             // R[(a y1' y1), (y2 b y2')]
             DT R(ctx, {Dz * Dy, Dy * Dy, Dz * Dy});
             if (oz) {
@@ -313,15 +371,16 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
                     TNR_CUDA(cudaEventCreate(&e1));
                     TNR_CUDA(cudaEventRecord(e0, ctx->stream));
                 }
-                ozaki_multiply(ctx, Q8, Pk8[d], R.p, mdim);
+                ozaki_multiply(ctx, Q8, Pk8[d - d0], R.p, mdim);
                 if (ctx->time_gemm) {
                     TNR_CUDA(cudaEventRecord(e1, ctx->stream));
                     ctx->gemm_events.emplace_back(e0, e1);
                     ctx->timed_flops += 2.0 * mdim * mdim * (double)kdim;
                 }
             } else
-            gemm(ctx, 'T', 'N', (int)mdim, (int)mdim, (int)kdim, 1.0, Qk.p, kdim, Pk[d].p, kdim,
+            gemm(ctx, 'T', 'N', (int)mdim, (int)mdim, (int)kdim, 1.0, Qk.p, kdim, Pk[d - d0].p, kdim,
                  0.0, R.p, mdim);
+            PhaseScope ph_uy(ctx, "hotrg3d.uy_scatter");
             // S[(a y1'), e, (b y2')] = sum_(y1 y2) R[(a y1'), (y1 y2), (b y2')] Uy[(y1 y2), e]
             DT S(ctx, {Dz, Dy, ny, Dz, Dy});
             GemmBatch bt;
@@ -350,6 +409,7 @@ void hotrg3d_substep(Context* ctx, const DT& T, int chi, DT& Tout, long long f0,
         if (oz) ozaki_free(ctx, Q8);
     }
     for (auto& o : Pk8) ozaki_free(ctx, o);
+    }
 }
 
 // full step! (hotrg3d.jl:131-139) on one GPU

@@ -412,8 +412,11 @@ class HOTRG_3D(_Sym3D, TNRScheme):
     PERM = (5, 3, 1, 2, 0, 4)  # ((6,4),(2,3,1,5))
 
     def __init__(self, T, ctx=None, shard=None, group=None, peer_scatter=None, symmetric=None,
-                 max_chunk_elems=1 << 29):
+                 max_chunk_elems=1 << 29, split_projectors=True):
         self.group = group
+        # sharded runs: deal the four projector eigendecompositions to the ranks instead of
+        # repeating them on every rank (False = round-1 behaviour, for A/B measurements)
+        self.split_projectors = split_projectors if split_projectors == "force" else bool(split_projectors)
         self.max_chunk_elems = int(max_chunk_elems)
         is_sym = self._init_sym3d(T, symmetric, ctx)
         if not is_sym:
@@ -454,6 +457,35 @@ class HOTRG_3D(_Sym3D, TNRScheme):
         self._symm = (bufs, hdls)
         return self._symm
 
+    def _projector_halves(self, chi, od, world, rank):
+        """The four truncated eigendecompositions of a z-compression (hotrg3d.jl:83-108), dealt
+        round-robin to the ranks: half h is computed by rank h % world
+        (`tnr_hotrg3d_proj_half`) and broadcast -- 4 small messages (D^2 x chi doubles) instead
+        of every rank repeating the Gram contractions and eigensolves.  Every half is computed
+        by ONE rank with the kernels a single-GPU run uses, so the result is bit-identical."""
+        import torch
+        import torch.distributed as dist
+
+        d = self.T.dims
+        sx = d[5] * d[5] * od[3] + 1
+        sy = d[4] * d[4] * od[2] + 1
+        sizes = (sx, sx, sy, sy)
+        offs = (0, sx, 2 * sx, 2 * sx + sy)
+        buf = torch.empty(2 * sx + 2 * sy, dtype=torch.float64, device=self.ctx.torch_device)
+        for h in range(4):
+            if h % world == rank:
+                self.ctx.call("tnr_hotrg3d_proj_half", self.T.ptr, _lib.i64(d), chi, h,
+                              C.c_void_p(buf.data_ptr() + 8 * offs[h]))
+        if world > 1:
+            self.ctx.synchronize()      # engine stream -> torch stream hand-over
+            for h in range(4):
+                src = h % world
+                if self.group is not None:
+                    src = dist.get_global_rank(self.group, src)
+                dist.broadcast(buf[offs[h]: offs[h] + sizes[h]], src=src, group=self.group)
+            torch.cuda.current_stream().synchronize()
+        return buf
+
     def _substep(self, chi):
         import torch.distributed as dist
 
@@ -478,20 +510,31 @@ class HOTRG_3D(_Sym3D, TNRScheme):
                 log.warning("symmetric memory unavailable (%s); using the NCCL all-gather", e)
                 self.peer_scatter = False
                 use_peers = False
+        split = self.split_projectors == "force" or (world > 1 and self.split_projectors)
+        halves = self._projector_halves(chi, od, world, rank) if split else None
         if use_peers:
             turn = self._symm_turn
             self._symm_turn ^= 1
             buf, hdl = bufs[turn], hdls[turn]
             ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
-            self.ctx.call("tnr_hotrg3d_substep_peers", self.T.ptr, _lib.i64(d), chi, ptrs, world,
-                          rank, dims_out, lo, hi)
+            if split:
+                self.ctx.call("tnr_hotrg3d_contract", self.T.ptr, _lib.i64(d), chi,
+                              C.c_void_p(halves.data_ptr()), ptrs, world, rank, dims_out, lo, hi)
+            else:
+                self.ctx.call("tnr_hotrg3d_substep_peers", self.T.ptr, _lib.i64(d), chi, ptrs,
+                              world, rank, dims_out, lo, hi)
             hdl.barrier()  # all ranks' peer stores have landed in this buffer
             out = DeviceTensor(buf, od, 2, self.ctx)
             self.T = out.permute(self.PERM)
             return
         out = DeviceTensor.empty(od, 2, self.ctx)
-        self.ctx.call("tnr_hotrg3d_substep", self.T.ptr, _lib.i64(d), chi, out.ptr, dims_out,
-                      lo, hi)
+        if split:
+            ptrs = (C.c_void_p * 1)(int(out.buf.data_ptr()))
+            self.ctx.call("tnr_hotrg3d_contract", self.T.ptr, _lib.i64(d), chi,
+                          C.c_void_p(halves.data_ptr()), ptrs, 1, 0, dims_out, lo, hi)
+        else:
+            self.ctx.call("tnr_hotrg3d_substep", self.T.ptr, _lib.i64(d), chi, out.ptr, dims_out,
+                          lo, hi)
         if world > 1:
             allgather_last_leg(out.buf, od, self.group)
         self.T = out.permute(self.PERM)

@@ -153,9 +153,10 @@ class SymTensor:
             lst.append((key, off, math.prod(l.dims[q] for l, q in zip(legs, key))))
         return out
 
-    def matricize(self, rows, cols):
+    def matricize(self, rows, cols, transposed=False):
         """Coupled-sector matrices M_c (rows_c x cols_c) for the bipartition rows | cols.
-        Returns (mats, row_tuples, col_tuples)."""
+        Returns (mats, row_tuples, col_tuples).  transposed=True stores M_c^T (cols_c x rows_c,
+        i.e. the COLUMN index contiguous): the K-contiguous operand layout of the TMA GEMM."""
         import torch
 
         rt, ct = self._tuples(rows, False), self._tuples(cols, True)
@@ -166,7 +167,7 @@ class SymTensor:
             nr = rt[c][-1][1] + rt[c][-1][2]
             nc = ct[c][-1][1] + ct[c][-1][2]
             buf = torch.zeros(nr * nc, dtype=torch.float64, device=self.ctx.torch_device)
-            mats[c] = DeviceTensor(buf, (nr, nc), 1, self.ctx)
+            mats[c] = DeviceTensor(buf, (nc, nr) if transposed else (nr, nc), 1, self.ctx)
         rlook = {c: {k: (o, s) for k, o, s in v} for c, v in rt.items()}
         clook = {c: {k: (o, s) for k, o, s in v} for c, v in ct.items()}
         for key, blk in self.blocks.items():
@@ -176,7 +177,10 @@ class SymTensor:
             M = mats[c]
             roff, _ = rlook[c][rk]
             coff, _ = clook[c][ck]
-            self._copy_block(blk, key, rows, cols, M, roff, coff, to_matrix=True)
+            if transposed:   # the same copy with the roles of the two index groups exchanged
+                self._copy_block(blk, key, cols, rows, M, coff, roff, to_matrix=True)
+            else:
+                self._copy_block(blk, key, rows, cols, M, roff, coff, to_matrix=True)
         return mats, rt, ct
 
     def _copy_block(self, blk, key, rows, cols, M, roff, coff, to_matrix):
@@ -233,7 +237,9 @@ def sym_contract(A: SymTensor, la: str, B: SymTensor, lb: str, lc: str) -> SymTe
         assert x.same_space(y), f"contracted leg '{c}': sector structure differs"
     rows_a, cols_a = [la.index(c) for c in fa], [la.index(c) for c in K]
     rows_b, cols_b = [lb.index(c) for c in K], [lb.index(c) for c in fb]
-    Am, art, _ = A.matricize(rows_a, cols_a)
+    # A is stored transposed (K x M, K contiguous) and B as K x N: both operands K-contiguous, the
+    # layout of the TMA + mbarrier GEMM (`tnr_gemm_grouped("T", "N")`: one launch for all sectors)
+    Am, art, _ = A.matricize(rows_a, cols_a, transposed=True)
     Bm, _, bct = B.matricize(rows_b, cols_b)
     import torch
 
@@ -242,16 +248,16 @@ def sym_contract(A: SymTensor, la: str, B: SymTensor, lb: str, lc: str) -> SymTe
     for c in Am:
         if c not in Bm:
             continue
-        m, k = Am[c].dims
+        k, m = Am[c].dims
         k2, n = Bm[c].dims
         assert k == k2
         buf = torch.empty(m * n, dtype=torch.float64, device=ctx.torch_device)
         Cm[c] = DeviceTensor(buf, (m, n), 1, ctx)
-        probs.append(_lib.GemmProblem(m, n, k, Am[c].buf.data_ptr(), m, Bm[c].buf.data_ptr(), k,
+        probs.append(_lib.GemmProblem(m, n, k, Am[c].buf.data_ptr(), k, Bm[c].buf.data_ptr(), k,
                                       buf.data_ptr(), m))
     if probs:
         arr = (_lib.GemmProblem * len(probs))(*probs)
-        ctx.call("tnr_gemm_grouped", b"N", b"N", len(probs), arr, 1.0, 0.0)
+        ctx.call("tnr_gemm_grouped", b"T", b"N", len(probs), arr, 1.0, 0.0)
     # split the sector matrices into tuple blocks, directly in the requested leg order
     out_legs_nat = [A.legs[i] for i in rows_a] + [B.legs[i] for i in cols_b]
     nat = fa + fb
@@ -386,10 +392,12 @@ def btrg_step_sym(T: SymTensor, S1, S2, k: float, chi: int):
     """step!(::BTRG) on a Z_N tensor -- src/schemes/btrg.jl:62-97.  S1, S2: {charge: diag}."""
     pa = (1.0 - k) / 2.0
     U, S, V, _ = sym_svd_trunc(T, 2, chi)
+    LAST_SPECTRA["btrg"] = [S]
     Sa, S1n = vec_map(S, 2, pa), vec_map(S, 2, k)
     A = U.scale_leg(2, Sa)            # [p s c]  (btrg labels A[6 5;-3])
     B = V.scale_leg(0, Sa)            # [b q r]
     U2, Sv, V2, _ = sym_svd_trunc(T.permute((2, 0, 3, 1)), 2, chi)
+    LAST_SPECTRA["btrg"].append(Sv)
     Sa2, S2n = vec_map(Sv, 2, pa), vec_map(Sv, 2, k)
     Cc = U2.scale_leg(2, Sa2)         # [s r d]
     D = V2.scale_leg(0, Sa2)          # [a p q]
