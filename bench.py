@@ -47,6 +47,15 @@ NOMINAL_FP64_TFLOPS = 40.0      # B200 FP64 tensor peak (vendor figure; no measu
 DMMA_FMA_PER_CLK_SM = 64        # DMMA.8x8x4 pipe: 64 FP64 FMA / clk / SM (148 SMs)
 
 METRIC = "HOTRG_3D Ising chi=%d s/RG-step"
+METRIC_ATRG = "ATRG_3D Ising chi=%d s/RG-step"
+
+
+def _atrg_stats():
+    try:
+        from tnrkit.jl_b200 import atrg3d_factored as af
+        return json.loads(json.dumps(af.LAST_STATS, default=str))
+    except Exception:
+        return None
 
 
 def log(*a):
@@ -321,9 +330,29 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
-    scheme = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=world > 1)
+    atrg = args.workload == "atrg3d"
+    if atrg:
+        # BASELINE.json configs[3]: ATRG_3D, factored step (no chi^6 object), chunks of the open
+        # bond sharded over the ranks; a dense step is used below chi = 40 unless --factored
+        scheme = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=world > 1,
+                            factored=True if (world > 1 or args.factored or
+                                              tk.ATRG_3D.wants_factored(chi)) else False,
+                            rfactor=args.rfactor)
+    else:
+        scheme = tk.HOTRG_3D(tk.classical_ising_3D(tk.Trivial), shard=world > 1)
     trunc = tk.truncrank(chi)
     norms = [scheme.finalize()]
+
+    def state_bufs():
+        """Device buffers holding the scheme's tensor (what a host would upload per step)."""
+        F = getattr(scheme, "factors", None)
+        if F is not None:
+            return [F.P.buf[:F.P.size], F.Q.buf[:F.Q.size]]
+        return [scheme.T.buf[:scheme.T.size]]
+
+    def state_dims():
+        F = getattr(scheme, "factors", None)
+        return tuple(F.dims) if F is not None else tuple(scheme.T.dims)
 
     def barrier():
         if world > 1:
@@ -331,7 +360,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def saturated():
-        return all(d == chi for d in scheme.T.dims)
+        return all(d == chi for d in state_dims())
 
     # ---- warm-up: RG iterations 1..W (untimed) -------------------------------------------
     w_done = 0
@@ -348,14 +377,15 @@ def run_gpu(args):
         last = time.perf_counter() - t0
         w_done += 1
         if rank == 0:
-            log(f"warm-up step {w_done}/{args.warmup}: dims {scheme.T.dims} norm "
+            log(f"warm-up step {w_done}/{args.warmup}: dims {state_dims()} norm "
                 f"{norms[-1]:.6e} {last:.1f}s (t+{time.time() - T_START:.0f}s)")
     if rank == 0 and not saturated():
-        log(f"WARNING: bond dimensions not yet saturated after warm-up: {scheme.T.dims}")
+        log(f"WARNING: bond dimensions not yet saturated after warm-up: {state_dims()}")
 
     # ---- timed steps: RG iterations W+1.. ------------------------------------------------
-    nelem = scheme.T.size
-    pinned = torch.empty(max(nelem, chi ** 6), dtype=torch.float64, pin_memory=True)
+    nelem = sum(b.numel() for b in state_bufs())
+    pinned = torch.empty(max(nelem, 2 * chi ** 5 if atrg else chi ** 6), dtype=torch.float64,
+                         pin_memory=True)
     sampler = ClockSampler(local)
     ctx.reset_counters()
     ctx.gemm_timing(True)
@@ -379,14 +409,23 @@ def run_gpu(args):
                 break
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         # stage the step's input on the host (untimed), then time H2D + step + finalize
-        nelem = scheme.T.size
-        pinned[:nelem].copy_(scheme.T.buf[:nelem])
+        bufs = state_bufs()
+        nelem = sum(b.numel() for b in bufs)
+        if nelem > pinned.numel():
+            pinned = torch.empty(nelem, dtype=torch.float64, pin_memory=True)
+        off = 0
+        for b in bufs:
+            pinned[off:off + b.numel()].copy_(b)
+            off += b.numel()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         e[0].record()
-        scheme.T.buf[:nelem].copy_(pinned[:nelem], non_blocking=True)
+        off = 0
+        for b in bufs:
+            b.copy_(pinned[off:off + b.numel()], non_blocking=True)
+            off += b.numel()
         e[1].record()
         scheme.step(trunc)
         norms.append(scheme.finalize())  # device->host read of the step's result (the norm)
@@ -421,15 +460,15 @@ def run_gpu(args):
         K = k_done
         sec = dev_ms / 1e3 / K
         e2e_sec = e2e_ms / 1e3 / K
-        fl = step_flops(chi) if saturated() else None
+        fl = step_flops(chi) if (saturated() and not atrg) else None
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         clock_peak = 148 * DMMA_FMA_PER_CLK_SM * 2 * sm_mhz * 1e6 / 1e12
         cpu_v = cpu_cores = cpu_sample_desc = cpu_val = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not atrg:
             cpu_v, cpu_cores, cpu_sample_desc, cpu_val = cpu_sample(chi)
         out = {
-            "metric": METRIC % chi, "value": sec, "unit": "s/RG-step", "n_gpus": world,
+            "metric": (METRIC_ATRG if atrg else METRIC) % chi, "value": sec, "unit": "s/RG-step", "n_gpus": world,
             "steps": K, "warmup": w_done, "steps_requested": args.steps,
             "warmup_requested": args.warmup, "ms_per_step": dev_ms / K,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -441,9 +480,11 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {
                 "engine": args.engine,
-                "workload": f"HOTRG_3D on classical_ising_3D(Trivial, beta_c) truncrank({chi}); "
-                            f"timed steps are RG iterations {first_iter}.."
-                            f"{first_iter + K - 1} of run! (legs {scheme.T.dims})",
+                "workload": f"{'ATRG_3D' if atrg else 'HOTRG_3D'} on classical_ising_3D(Trivial, "
+                            f"beta_c) truncrank({chi}); timed steps are RG iterations "
+                            f"{first_iter}..{first_iter + K - 1} of run! (legs {state_dims()})" +
+                            (f"; {'factored' if scheme.factors is not None else 'dense'} step, "
+                             f"R factors: {args.rfactor}" if atrg else ""),
                 "time_budget_s": budget,
                 "time_box": (f"{K} of {args.steps} requested timed steps and {w_done} of "
                              f"{args.warmup} requested warm-up iterations fit the wall budget; "
@@ -451,12 +492,16 @@ def run_gpu(args):
                              "a steady-state step") if (K < args.steps or w_done < args.warmup)
                 else "all requested steps ran",
                 "parallelism": "1 GPU" if world == 1 else
-                f"open x-bond sharded over {world} GPUs; exchange: " +
+                (f"chunks of the open bond of AX / YD dealt to {world} GPUs; all-gathers of the "
+                 "chunk R factors and of H / G (NCCL)") if atrg else
+                f"open x-bond sharded over {world} GPUs; projector halves dealt to the ranks "
+                "and broadcast; exchange: " +
                 ("every T' slab stored to all ranks over NVLink by the kernel that produces it "
                  f"({peer_launches} fused scatter launches, symmetric memory), no collective"
                  if peer_launches else "1 NCCL all-gather per z-compression"),
-                "l2": "inputs (chi^6 doubles = %.2f GB) exceed L2; no flush needed" %
-                      (scheme.T.size * 8 / 1e9),
+                "l2": "working set (%.2f GB of chi^6 / chunk tensors) exceeds L2; no flush needed" %
+                      (chi ** 6 * 8 / 1e9),
+                "gemm_flop_per_step": ctr["gemm_flops"] / K,
                 "steps_per_s": 1.0 / sec,
                 "step_flop": fl,
                 "step_tflops": (fl / sec / 1e12) if fl else None,
@@ -468,6 +513,7 @@ def run_gpu(args):
                 # reference tests against (test/schemes.jl:11, f = -3.507, rtol 1e-3)
                 "free_energy": tk.free_energy(norms, tk.ising_βc_3D, scalefactor=8.0),
                 "free_energy_benchmark": -3.507,
+                "atrg3d_stats": _atrg_stats() if atrg else None,
                 "wall_s_timed_region": wall,
                 "wall_s_since_start": time.time() - T_START,
                 "cpu_flop_model_validation": cpu_val,
@@ -493,7 +539,10 @@ def run_gpu(args):
                 # dram bytes of one launch are an ncu quantity and are not measured by this
                 # run: see profiles/ (ncu --set full raw export of this kernel)
                 "traffic": None,
-                "kernel": ("gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
+                "kernel": ("DMMA GEMM launches above 1e11 flop of the factored ATRG_3D step "
+                           "(gemm_dmma_tma_kernel / gemm_dmma_kernel: chunk contractions, TSQR "
+                           "Gram products, subspace iterations)") if atrg else
+                          ("gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
                            "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
                            "projector Gram GEMMs above 1e11 flop)") if args.engine == "dmma" else
                           ("ozaki_tile_kernel (tcgen05.mma kind::i8, TMEM accumulators; achieved = "
@@ -524,6 +573,11 @@ def main():
                     help="wall seconds from interpreter start within which the run must end "
                          "(0 = run exactly --steps / --warmup)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hotrg3d", choices=["hotrg3d", "atrg3d"],
+                    help="hotrg3d: the headline (BASELINE.json metric, configs[4], chi=24); atrg3d: "
+                         "configs[3] (use --chi 48), same time box and JSON contract")
+    ap.add_argument("--rfactor", default="tsqr", choices=["tsqr", "gram"])
+    ap.add_argument("--factored", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--crt-moduli", type=int, default=16)
     ap.add_argument("--engine", default="dmma", choices=["dmma", "ozaki", "ozaki_crt"],

@@ -53,7 +53,8 @@ int tnr_get_tma_launches(tnr_context* ctx, uint64_t* tma_gemm_launches);
 int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
 /* engine options: "disable_tma" = 1 forces the cp.async GEMM for every layout (A/B tests);
  * "disable_subspace", "disable_block_jacobi", "disable_precondition" switch the fast SVD/eigh
- * paths off; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes;
+ * paths off; "disable_qr" = 1 replaces the Householder QR stage of tall problems by the round-1
+ * Gram-preconditioned Jacobi; "ozaki" = S (0 = off, default) enables the INT8 emulation engine with S planes;
  * "ozaki_crt" = N (0 = off, default; 14..18) selects its CRT variant with N moduli instead;
  * "permute_bulk" = 1 (default) | 0: the TMA-fed tiled copy kernel (cp.async.bulk reads) for every
  * strided copy whose source pieces are 16-byte aligned; "permute_unroll" = 1 | 2 | 4 (default) and
@@ -150,9 +151,17 @@ int tnr_contract(tnr_context* ctx, const double* A, int rankA, const int64_t* di
  * k = min(chi, min(rows, cols)).  U: rows x k, S: k, Vt: k x cols, eps: 2-norm of discarded. */
 int tnr_svd_trunc(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
                   int chi, double* U, double* S, double* Vt, int64_t* k_out, double* eps_out);
+/* Thin QR of a tall column-major matrix A (m x n, m >= n): blocked Householder (panels of 32
+ * columns, compact WY, trailing update as FP64 tensor-core GEMMs) -- the factorization behind
+ * TensorKit `left_orth` / `right_orth` (src/schemes/atrg3d.jl:53-56) and the first stage of the
+ * truncated SVD of tall matrices (QR, then one-sided Jacobi of R in shared memory, then the
+ * top-chi selection).  Q (m x n, orthonormal columns) and / or R (n x n upper triangular, LAPACK
+ * sign convention) may be NULL. */
+int tnr_qr(tnr_context* ctx, const double* A, int64_t m, int64_t n, double* Q, double* R);
 /* The factor R of `_, R = left_orth(T)` (src/schemes/atrg3d.jl:53-56) for a tall matricization
- * (rows = first `ncod` legs >= cols), up to the orthogonal gauge on its new bond, which cancels
- * in the projectors built from it (atrg3d.jl:58-66): R = Sigma V^T, cols x cols, R^T R = T^T T.
+ * (rows = first `ncod` legs >= cols): the upper-triangular Householder R (cols x cols,
+ * R^T R = T^T T); with the option "disable_qr" the round-1 form R = Sigma V^T, which differs by an
+ * orthogonal gauge on the new bond that cancels in the projectors built from it (atrg3d.jl:58-66).
  * The isometry Q is never formed.  Used chunk by chunk (TSQR) by the factored ATRG_3D step. */
 int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
                double* R);

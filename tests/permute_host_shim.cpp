@@ -20,7 +20,8 @@ static int run_bulk(const double* src, double* dst, const BulkPlan& bp, long lon
     if ((uintptr_t)tile_buf % 16) ++tile_buf;
     int bad = 0;
     const long long tile_elems = bulk_tile_elems(p);
-    if ((size_t)(tile_elems * p.tpc) * sizeof(double) != bp.smem || p.tpc < 1 || p.tpc > BULK_MAX_TPC)
+    if ((size_t)(tile_elems * p.tpc) * sizeof(double) + (p.tab_smem ? sizeof(BulkLaneTab) * 32 : 0) != bp.smem ||
+        p.tpc < 1 || p.tpc > BULK_MAX_TPC)
         return -4;
     info[2] = p.ntiles;
     for (long long b = 0; b < bp.blocks; ++b) {

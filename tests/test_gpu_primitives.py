@@ -306,3 +306,75 @@ def test_gemm_grouped_tma_declines_small_or_unaligned(tk, ctx):
         assert _counter(ctx, "tma_grouped_launches") == t0      # too few tiles / odd leading dim
         for (dA, dB, dC), ref in zip(keep, refs):
             assert np.abs(dC.to_numpy() - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("m,n", [(64, 32), (1000, 96), (5000, 100), (4097, 33), (300, 300), (20000, 256),
+                                 (500, 7), (33, 1), (70000, 64), (2048, 577)])
+def test_blocked_householder_qr(tk, ctx, m, n):
+    """`tnr_qr` (qr.cu: panels of 32 Householder columns, compact WY, DMMA trailing update) against
+    numpy / LAPACK geqrf: same R up to rounding INCLUDING signs (dlarfg convention), Q orthonormal
+    to rounding, Q R = A."""
+    rng = np.random.default_rng(m + n)
+    A = rng.standard_normal((m, n))
+    dA = _up(tk, A)
+    dQ, dR = tk.DeviceTensor.empty((m, n)), tk.DeviceTensor.empty((n, n))
+    q0 = _counter(ctx, "qr_factorizations")
+    ctx.call("tnr_qr", dA.ptr, m, n, dQ.ptr, dR.ptr)
+    assert _counter(ctx, "qr_factorizations") == q0 + 1
+    Q, R = dQ.to_numpy(), dR.to_numpy()
+    assert np.array_equal(np.tril(R, -1), np.zeros_like(R))
+    scale = np.linalg.norm(A)
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 5e-14
+    assert np.linalg.norm(Q @ R - A) <= 1e-14 * scale * np.sqrt(n)
+    Rn = np.linalg.qr(A, mode="r")
+    assert np.abs(R - Rn).max() <= 1e-12 * scale
+
+
+def test_qr_rank_deficient_and_graded(tk, ctx):
+    rng = np.random.default_rng(9)
+    m, n = 3000, 80
+    A = rng.standard_normal((m, n))
+    A[:, 10] = 0.0                      # a zero column
+    A[:, 20] = A[:, 5]                  # a duplicate
+    A[:, 40:] *= 10.0 ** -np.arange(40)[None, :]     # graded over 40 orders of magnitude
+    dA = _up(tk, A)
+    dQ, dR = tk.DeviceTensor.empty((m, n)), tk.DeviceTensor.empty((n, n))
+    ctx.call("tnr_qr", dA.ptr, m, n, dQ.ptr, dR.ptr)
+    Q, R = dQ.to_numpy(), dR.to_numpy()
+    assert np.isfinite(Q).all() and np.isfinite(R).all()
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 5e-14
+    # column-wise backward error (graded columns keep their relative accuracy)
+    err = np.linalg.norm(Q @ R - A, axis=0)
+    assert np.all(err <= 1e-14 * np.maximum(np.linalg.norm(A, axis=0), 1e-300) * 30 + 1e-300)
+
+
+@pytest.mark.parametrize("m,n,chi", [(6000, 96, 40), (2304, 576, 24), (40000, 64, 64)])
+def test_tall_svd_qr_path_equals_gram_jacobi_path_and_lapack(tk, ctx, m, n, chi):
+    """svd_trunc of a tall matrix: Householder QR + Jacobi of R (default) and the round-1
+    Gram-preconditioned Jacobi ("disable_qr") give the LAPACK spectrum to 1e-13 sigma_1, and the
+    QR path really ran."""
+    rng = np.random.default_rng(m)
+    A = rng.standard_normal((m, n)) @ np.diag(np.logspace(0, -9, n)) @ rng.standard_normal((n, n))
+    sref = np.linalg.svd(A, compute_uv=False)
+    out = {}
+    for mode in (0, 1):
+        ctx.set_option("disable_qr", mode)
+        ctx.set_option("disable_subspace", 1)
+        try:
+            q0 = _counter(ctx, "qr_factorizations")
+            U, S, Vt, eps = tk.svd_trunc(tk.DeviceTensor.from_numpy(A), 1, chi)
+            ran = _counter(ctx, "qr_factorizations") - q0
+        finally:
+            ctx.set_option("disable_qr", 0)
+            ctx.set_option("disable_subspace", 0)
+        assert (ran >= 1) == (mode == 0)
+        s = S.to_numpy()
+        assert np.abs(s - sref[:chi]).max() <= 1e-13 * sref[0]
+        u, vt = U.to_numpy(), Vt.to_numpy()
+        rec = (u * s) @ vt
+        best = np.linalg.svd(A, full_matrices=False)
+        ref = (best[0][:, :chi] * best[1][:chi]) @ best[2][:chi]
+        assert np.abs(rec - ref).max() <= 1e-11 * sref[0]
+        assert abs(eps - np.linalg.norm(sref[chi:])) <= 1e-12 * sref[0]
+        out[mode] = s
+    assert np.abs(out[0] - out[1]).max() <= 1e-13 * sref[0]

@@ -170,6 +170,7 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
         else if (std::strcmp(key, "disable_subspace") == 0) ctx->c.disable_subspace = value != 0;
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
+        else if (std::strcmp(key, "disable_qr") == 0) ctx->c.disable_qr = value != 0;
         else throw Error(1, std::string("unknown option: ") + key);
     });
 }
@@ -334,6 +335,14 @@ int tnr_svd_trunc(tnr_context* ctx, const double* T, int rank, const int64_t* di
         TNR_CUDA(cudaMemcpyAsync(&e, f.eps.p, 8, cudaMemcpyDeviceToHost, ctx->c.stream));
         TNR_CUDA(cudaStreamSynchronize(ctx->c.stream));
         if (eps_out) *eps_out = e;
+    });
+}
+
+int tnr_qr(tnr_context* ctx, const double* A, int64_t m, int64_t n, double* Q, double* R) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(A && m >= n && n >= 1 && (Q || R), "qr: bad arguments");
+        qr_thin(&ctx->c, A, m, n, Q, R);
     });
 }
 
@@ -703,6 +712,8 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;
+        else if (n == "qr_factorizations") *value = (double)c.qr_factorizations;
+        else if (n == "jacobi_not_converged") *value = (double)c.jacobi_not_converged;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;
         else if (n == "gemm_flops") *value = c.gemm_flops;
         else if (n == "permute_bytes") *value = c.permute_bytes;

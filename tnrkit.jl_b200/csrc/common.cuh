@@ -43,6 +43,8 @@ struct Counters {
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
+    unsigned long long qr_factorizations = 0;    // blocked Householder QR factorizations (qr.cu)
+    unsigned long long jacobi_not_converged = 0; // one-sided Jacobi runs that hit the sweep limit (an error is raised)
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
     double permute_bytes = 0.0;            // read+write bytes moved by permute kernels
@@ -62,11 +64,12 @@ struct Context {
     int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
     int permute_unroll = 4;  // 1 | 2 | 4: rows of the read phase in flight per thread in the fallback tiled kernel (r02: 4 measured 1.7x faster than 1)
     int permute_tpc = 8;       // max tiles per CTA of the TMA-fed copy (tuning)
-    int permute_chunk_below = 512;  // rows below this many bytes: cp.async chunks instead of bulk pieces (tuning)
+    int permute_chunk_below = 0;  // rows below this many bytes: cp.async chunks instead of bulk pieces (tuning)
     bool permute_bulk = true;  // TMA-fed tiled copy (cp.async.bulk) whenever the source pieces are 16-byte aligned
     int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
+    bool disable_qr = false;  // tall problems: Gram-preconditioned Jacobi (round 1) instead of Householder QR + Jacobi of R
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     // optional per-phase timing of the scheme bodies (same switch as time_gemm): name + events
@@ -185,6 +188,7 @@ void fill_zero(Context* ctx, double* A, long long n);
 void fill_random(Context* ctx, double* x, long long n, unsigned long long seed);
 void axpy(Context* ctx, double* y, const double* x, double alpha, long long n);  // y += alpha x
 void sum_squares(Context* ctx, const double* x, long long n, double* dev_out);   // deterministic
+void sqrt_inplace(Context* ctx, const double* dev_in, double* dev_out);          // *out = sqrt(max(*in, 0))
 // dot of two strided "vectors" with weights: out = |sum_{i,j..}|, used by BTRG finalize
 // dst = flag ? a : b, flag = (*epsA > *epsB)  (device side choice, HOTRG projector pick)
 void select_copy(Context* ctx, double* dst, const double* a, const double* b, long long n,

@@ -183,6 +183,14 @@ void fill_zero(Context* ctx, double* A, long long n) {
     TNR_CUDA(cudaMemsetAsync(A, 0, n * sizeof(double), ctx->stream));
 }
 
+__global__ void sqrt_scalar_kernel(const double* in, double* out) { *out = sqrt(fmax(*in, 0.0)); }
+
+void sqrt_inplace(Context* ctx, const double* dev_in, double* dev_out) {
+    sqrt_scalar_kernel<<<1, 1, 0, ctx->stream>>>(dev_in, dev_out);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
 void select_copy(Context* ctx, double* dst, const double* a, const double* b, long long n,
                  const double* eps_a, const double* eps_b, double* eps_out) {
     select_copy_kernel<<<nblk(n), 256, 0, ctx->stream>>>(dst, a, b, n, eps_a, eps_b, eps_out);

@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "tensor.hpp"
 
 namespace tnr {
 namespace {
@@ -315,6 +316,23 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
     // GEMM + a small n x n Jacobi) and rotate G <- G W, V <- V W by GEMM.  G W already has
     // nearly orthogonal columns, so the accurate one-sided sweeps below converge in 1-2 passes
     // over the tall matrix instead of ~10; accuracy is that of Jacobi on G W (W is orthogonal).
+    // Tall matrices, the design the north star names: blocked Householder QR (trailing update on
+    // the tensor cores, qr.cu), one-sided Jacobi on the small n x n factor R in shared memory
+    // (the block kernel below, via the recursive call), then G <- Q (R V).  The rotations only
+    // ever touch R; the tall matrix is read by the QR panels and written once by the GEMMs
+    // that apply Q.
+    if (!ctx->disable_qr && m >= 2 * n && n >= 32 && ldg == m && (!V || ldv == n)) {
+        TNR_CUDA(cudaFreeAsync(d_rot, ctx->stream));
+        dfree(ctx, d_f2);
+        QRWork w;
+        qr_factor(ctx, G, m, n, ldg, w);
+        double* R = dalloc(ctx, (size_t)n * n);
+        qr_copy_r(ctx, G, ldg, n, R, n);
+        const int sw = jacobi_orthogonalize(ctx, R, n, n, n, V, ldv);   // R <- R V_J
+        qr_q_times(ctx, w, R, n, n, G, ldg);                             // G <- Q [R V_J; 0]
+        dfree(ctx, R);
+        return sw;
+    }
     if (!ctx->disable_precondition && m >= 4 * n && n >= 32 && ldg == m && (!V || ldv == n)) {
         double* gram = dalloc(ctx, (size_t)n * n);
         double* W = dalloc(ctx, (size_t)n * n);
@@ -365,6 +383,7 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured = true;
         }
+        bool converged = false;
         for (; sweeps < max_sweeps; ++sweeps) {
             TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
             for (int round = 0; round < nblk_pad - 1; ++round) launch(round);
@@ -373,16 +392,21 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
             int rot = 0;
             TNR_CUDA(cudaMemcpyAsync(&rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             TNR_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (rot == 0) { ++sweeps; break; }
+            if (rot == 0) { ++sweeps; converged = true; break; }
         }
         TNR_CUDA(cudaFreeAsync(d_rot, ctx->stream));
         dfree(ctx, d_f2);
+        // a factorisation that did not converge must not flow silently into U / S / V
+        if (!converged) ctx->ctr.jacobi_not_converged++;
+        TNR_CHECK(converged, "one-sided Jacobi did not converge in 40 sweeps (" +
+                                 std::to_string(m) + " x " + std::to_string(n) + ")");
         return sweeps;
     }
     // tall problems: a Gram GEMM (2 m n^2 flop on the tensor cores) is far cheaper than a sweep
     // (n-1 passes over the m x n matrix), so convergence is tested on the Gram matrix before
     // every sweep -- a preconditioned problem usually needs zero or one sweep.
     const bool gram_check = !ctx->disable_precondition && m >= 4 * n && n >= 32 && ldg == m;
+    bool converged = false;
     for (; sweeps < max_sweeps; ++sweeps) {
         if (gram_check) {
             double* gram = dalloc(ctx, (size_t)n * n);
@@ -396,7 +420,7 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
             TNR_CUDA(cudaMemcpyAsync(&viol, d_rot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             TNR_CUDA(cudaStreamSynchronize(ctx->stream));
             dfree(ctx, gram);
-            if (viol == 0) break;
+            if (viol == 0) { converged = true; break; }
         }
         TNR_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(int), ctx->stream));
         for (int round = 0; round < npad - 1; ++round) {
@@ -414,10 +438,17 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
         TNR_CUDA(cudaStreamSynchronize(ctx->stream));
         if (rot == 0) {
             ++sweeps;
+            converged = true;
             break;
         }
     }
     TNR_CUDA(cudaFreeAsync(d_rot, ctx->stream));
+    if (!converged) {
+        ctx->ctr.jacobi_not_converged++;
+        dfree(ctx, d_f2);
+        TNR_CHECK(false, "one-sided Jacobi did not converge in 40 sweeps (" + std::to_string(m) +
+                             " x " + std::to_string(n) + ")");
+    }
     dfree(ctx, d_f2);
     return sweeps;
 }

@@ -136,9 +136,12 @@ template <int VEC>
 __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict__ src,
                                                         double* __restrict__ dst,
                                                         const BulkParams p) {
-    extern __shared__ __align__(16) double tile[];
+    extern __shared__ __align__(16) double dyn_smem[];
     __shared__ unsigned long long bar_storage[BULK_MAX_TPC];
     __shared__ BulkGeom sgeom[BULK_MAX_TPC];
+    // dynamic shared memory: [lane table (32 entries, small tiles only)] [tpc tiles]
+    BulkLaneTab* stab = reinterpret_cast<BulkLaneTab*>(dyn_smem);
+    double* tile = dyn_smem + (p.tab_smem ? (sizeof(BulkLaneTab) * 32) / sizeof(double) : 0);
     const long long t0 = (long long)blockIdx.x * p.tpc;
     const int nt = (int)min((long long)p.tpc, p.ntiles - t0);
     const long long tile_elems = bulk_tile_elems(p);
@@ -153,6 +156,10 @@ __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         }
+    } else if (warp == 1 && p.tab_smem) {
+        BulkLaneTab tl;
+        bulk_lane_table(p, p.TV, p.TJ1, p.TJ1 * p.TJ2, lane, VEC, tl);
+        stab[lane] = tl;
     }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
@@ -169,7 +176,8 @@ __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict
     }
     // the write-phase slots of a full tile, computed while the loads are in flight
     BulkLaneTab full_tab;
-    bulk_lane_table(p, p.TV, p.TJ1, p.TJ1 * p.TJ2, lane, VEC, full_tab);
+    if (p.tab_smem) full_tab = stab[lane];
+    else bulk_lane_table(p, p.TV, p.TJ1, p.TJ1 * p.TJ2, lane, VEC, full_tab);
     if (p.chunked) {
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");

@@ -199,6 +199,12 @@ constexpr int BULK_KMAX = 6;          // elements (of VEC doubles) per lane and 
 constexpr int BULK_TILE_ELEMS = 9216; // doubles per tile (72 KB): 3 CTAs per SM
 constexpr int BULK_MAX_TPC = 8;       // tiles per CTA
 
+struct BulkLaneTab {
+    int so[BULK_KMAX];        // shared-memory offset of the slot (doubles), -1 = unused
+    int ri[BULK_KMAX];        // row of the pass the slot belongs to
+    long long dof[BULK_KMAX]; // destination offset relative to the pass origin
+};
+
 struct BulkParams {
     int rank;
     long long dims[MAXR], ss[MAXR], ds[MAXR];
@@ -213,6 +219,7 @@ struct BulkParams {
     int R;                  // i1 rows written per warp pass (short destination runs are batched)
     int tpc;                // tiles per CTA (small tiles: several in flight per CTA)
     int chunked;            // 1: rows shorter than 512 B are fetched as 16-byte cp.async chunks
+    int tab_smem;           // 1: the lane table is computed by one warp and shared (small tiles)
     long long ntiles;       // total number of tiles (grid = ceil(ntiles / tpc))
 };
 
@@ -236,7 +243,8 @@ inline int bulk_pick_extent(long long n, long long tgt, bool want_even) {
 // the copy does not have the structure / alignment the bulk kernel needs.
 struct BulkTuning {
     int max_tpc = BULK_MAX_TPC;     // tiles per CTA (1 = one tile per CTA)
-    int chunk_below = 512;          // whole-row pieces below this many bytes use cp.async chunks
+    int chunk_below = 0;            // whole-row pieces below this many bytes use cp.async chunks
+    //                                 (0 = never: measured equal to bulk pieces, more instructions)
 };
 
 inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_addr,
@@ -366,10 +374,14 @@ inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_ad
     // keep at least ~4 CTAs per SM worth of blocks
     while (tpc > 1 && p.ntiles / tpc < 148 * 4) --tpc;
     p.tpc = (int)tpc;
+    // several tiles per CTA: the per-lane slot table of the write phase is computed by ONE warp
+    // and shared (its integer divisions were 65 % issue utilisation on 18 KB tiles)
+    p.tab_smem = (tpc > 1 && tile_smem * (size_t)tpc + sizeof(BulkLaneTab) * 32 <=
+                                 BULK_TILE_ELEMS * sizeof(double)) ? 1 : 0;
     // whole-row pieces below 512 bytes go through 16-byte cp.async chunks instead of one bulk
     // request per piece
     p.chunked = (p.contig2 && row * 8 < tune.chunk_below) ? 1 : 0;
-    out.smem = tile_smem * (size_t)tpc;
+    out.smem = tile_smem * (size_t)tpc + (p.tab_smem ? sizeof(BulkLaneTab) * 32 : 0);
     out.blocks = (p.ntiles + tpc - 1) / tpc;
     out.ok = true;
     return out;
@@ -473,11 +485,6 @@ TNR_HD void bulk_load_phase(const BulkGeom& g, const BulkParams& p, double* tile
 // and slot.  The table depends only on the tile's (tv, tj1, cj), i.e. it is the same for every
 // full tile: the kernel computes it once per CTA (warp 0 -> shared memory) instead of once per
 // thread and tile -- the integer divisions here were the limiter of small tiles.
-struct BulkLaneTab {
-    int so[BULK_KMAX];        // shared-memory offset of the slot (doubles), -1 = unused
-    int ri[BULK_KMAX];        // row of the pass the slot belongs to
-    long long dof[BULK_KMAX]; // destination offset relative to the pass origin
-};
 
 TNR_HD void bulk_lane_table(const BulkParams& p, int tv, int tj1, int cj, int lane, int vec,
                             BulkLaneTab& T) {
@@ -490,7 +497,7 @@ TNR_HD void bulk_lane_table(const BulkParams& p, int tv, int tj1, int cj, int la
         T.ri[k] = 0;
         T.dof[k] = 0;
         if (e < R * run) {
-            const unsigned rr = e / run, x = e - rr * run;
+            const unsigned rr = (R == 1) ? 0u : e / run, x = e - rr * run;
             const unsigned jj = (tv == 1) ? x : x / (unsigned)tv;
             const unsigned v = x - jj * (unsigned)tv;
             const unsigned j2 = (cj == tj1) ? 0u : jj / (unsigned)tj1;

@@ -59,6 +59,23 @@ struct DT {
     }
 };
 
+// ---- qr.cu: blocked Householder QR (DMMA trailing update) ----
+struct QRWork {
+    long long m = 0, n = 0;
+    DT V;     // explicit reflectors, m x n, unit lower trapezoidal (ld = m)
+    DT T;     // compact-WY T blocks, 32 x 32 x ceil(n / 32)
+    DT tau;   // n
+};
+// A (m x n, lda, m >= n) in place: R in the upper triangle; reflectors kept in w
+void qr_factor(Context* ctx, double* A, long long m, long long n, long long lda, QRWork& w);
+void qr_copy_r(Context* ctx, const double* A, long long lda, long long n, double* R, long long ldr);
+// Y (m x k, ldy) <- Q Y ;  Y = Q [X; 0] for X n x k
+void qr_apply_q(Context* ctx, const QRWork& w, double* Y, long long ldy, long long k);
+void qr_q_times(Context* ctx, const QRWork& w, const double* X, long long ldx, long long k,
+                double* Y, long long ldy);
+
+void qr_thin(Context* ctx, const double* A, long long m, long long n, double* Q, double* R);
+
 DT clone(const DT& a);
 DT permute(const DT& a, const std::vector<int>& perm);
 // out labels = lc; contracted labels = those in both la and lb and not in lc

@@ -222,10 +222,33 @@ static Trunc eigh_trunc_jacobi(DT MM, int ncod, int chi) {
     return out;
 }
 
+// thin QR: Q (m x n, orthonormal columns), R (n x n upper triangular)
+void qr_thin(Context* ctx, const double* A, long long m, long long n, double* Q, double* R) {
+    TNR_CHECK(m >= n && n >= 1, "qr: expects a tall matrix");
+    DT W = clone(DT::view(ctx, const_cast<double*>(A), {m, n}));
+    QRWork w;
+    qr_factor(ctx, W.p, m, n, m, w);
+    if (R) qr_copy_r(ctx, W.p, m, n, R, n);
+    if (Q) {
+        DT I(ctx, {n, n});
+        set_identity(ctx, I.p, n);
+        qr_q_times(ctx, w, I.p, n, n, Q, m);
+    }
+}
+
 DT orth_r(const DT& T, int ncod) {
     Context* ctx = T.ctx;
     long long m = prod(T.d, 0, ncod), n = prod(T.d, ncod);
     TNR_CHECK(m >= n, "orth_r: expects a tall matrix");
+    if (!ctx->disable_qr) {
+        // the R factor itself: blocked Householder QR, trailing update on the tensor cores
+        DT A = clone(T);
+        QRWork w;
+        qr_factor(ctx, A.p, m, n, m, w);
+        DT R(ctx, {n, n});
+        qr_copy_r(ctx, A.p, m, n, R.p, n);
+        return R;
+    }
     DT G = clone(T);
     DT V(ctx, {n, n});
     set_identity(ctx, V.p, n);
@@ -270,6 +293,18 @@ void h2d(Context* ctx, double* dst, const double* src, size_t n) {
 // (columns of Y are expected to be roughly equilibrated; directions below 1e-14 relative
 // weight are dropped, i.e. set to zero).
 DT gram_orthonormalize(Context* ctx, const DT& Y, long long n, long long b) {
+    if (!ctx->disable_qr && n >= b) {
+        // Householder QR: Q = H_1 ... H_b [I; 0] is orthonormal to rounding whatever the
+        // conditioning of Y, and no b x b eigenproblem is solved
+        DT A = clone(DT::view(ctx, Y.p, {n, b}));
+        QRWork w;
+        qr_factor(ctx, A.p, n, b, n, w);
+        DT I(ctx, {b, b});
+        set_identity(ctx, I.p, b);
+        DT Q(ctx, {n, b});
+        qr_q_times(ctx, w, I.p, b, b, Q.p, n);
+        return Q;
+    }
     DT G(ctx, {b, b});
     gemm(ctx, 'T', 'N', (int)b, (int)b, (int)n, 1.0, Y.p, n, Y.p, n, 0.0, G.p, b);
     Trunc e = eigh_trunc_jacobi(std::move(G), 1, (int)b);
@@ -348,14 +383,21 @@ bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out)
                              ctx->stream));
     TNR_CUDA(cudaMemcpyAsync(out.S.p, Th.p, k * sizeof(double), cudaMemcpyDeviceToDevice,
                              ctx->stream));
-    // eps = ||discarded eigenvalues||_2: Ritz values k..b-1 explicitly, the rest from the
-    // Frobenius norm
-    double F2 = 0.0, kept = 0.0, mid = 0.0;
-    d2h(ctx, &F2, f2.p, 1);
-    for (long long j = 0; j < b; ++j) (j < k ? kept : mid) += theta[j] * theta[j];
-    double tail = std::max(0.0, F2 - kept - mid);
-    double eps = std::sqrt(mid + tail);
-    h2d(ctx, out.eps.p, &eps, 1);
+    // eps = ||discarded eigenvalues||_2 = ||MM - X_k Theta_k X_k^T||_F, evaluated on the deflated
+    // matrix itself (one n x n x k GEMM).  The round-1 form sqrt(||MM||_F^2 - sum theta^2) loses
+    // every digit once the tail drops below 1e-8 ||MM||_F, and eps decides HOTRG's
+    // `eps > eps'` projector choice (hotrg.jl:116, hotrg3d.jl:96): with the deflated norm the
+    // choice is made on values as accurate as the reference's full decomposition gives them.
+    {
+        DT D = clone(DT::view(ctx, MM.p, {n, n}));
+        DT XT(ctx, {n, k});
+        TNR_CUDA(cudaMemcpyAsync(XT.p, QS.p, n * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        diag_scale(ctx, XT.p, n, k, n, Th.p, false, 0, 0.0);
+        gemm(ctx, 'N', 'T', (int)n, (int)n, (int)k, -1.0, XT.p, n, QS.p, n, 1.0, D.p, n);
+        sum_squares(ctx, D.p, n * n, f2.p);
+        sqrt_inplace(ctx, f2.p, out.eps.p);
+    }
     ctx->ctr.subspace_eigh++;
     return true;
 }
@@ -467,11 +509,17 @@ bool svd_topk(Context* ctx, const DT& T, long long m, long long n, long long k, 
     long long dd[2] = {n, k};
     int pp[2] = {1, 0};
     permute(ctx, X.p, out.Vt.p, 2, dd, pp);  // first k columns of X, transposed -> k x n
-    double F2 = 0.0, kept = 0.0, mid = 0.0;
-    d2h(ctx, &F2, f2.p, 1);
-    for (long long j = 0; j < b; ++j) (j < k ? kept : mid) += sig[j] * sig[j];
-    double eps = std::sqrt(mid + std::max(0.0, F2 - kept - mid));
-    h2d(ctx, out.eps.p, &eps, 1);
+    // eps = ||A - U_k S_k V_k^T||_F on the deflated matrix (no cancellation, see eigh_topk)
+    {
+        DT D = clone(DT::view(ctx, T.p, {m, n}));
+        DT US(ctx, {m, k});
+        TNR_CUDA(cudaMemcpyAsync(US.p, Us.p, m * k * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        diag_scale(ctx, US.p, m, k, m, Sg.p, false, 0, 0.0);
+        gemm(ctx, 'N', 'T', (int)m, (int)n, (int)k, -1.0, US.p, m, X.p, n, 1.0, D.p, m);
+        sum_squares(ctx, D.p, m * n, f2.p);
+        sqrt_inplace(ctx, f2.p, out.eps.p);
+    }
     ctx->ctr.subspace_svd++;
     return true;
 }

@@ -19,11 +19,11 @@ cases = [("rotate ((6,4),(2,3,1,5))", (chi,) * 6, (5, 3, 1, 2, 0, 4)),
          ("ATRG_3D ((4,1),(2,3))-like", (chi,) * 6, (3, 0, 1, 2, 5, 4)),
          ("flat copy", (chi ** 6,), (0,))]
 # (bulk, unroll, tile[, tpc, chunk_below])
-variants = [(1, 4, 96, 8, 512), (1, 4, 96, 8, 0), (1, 4, 96, 1, 512), (1, 4, 96, 1, 0), (0, 4, 96)] if len(sys.argv) < 3 else \
+variants = [(1, 4, 96, 8, 0), (1, 4, 96, 8, 512), (1, 4, 96, 1, 0), (0, 4, 96)] if len(sys.argv) < 3 else \
     [(0, 1, 96), (0, 2, 96), (0, 4, 96), (0, 4, 64), (0, 4, 48), (0, 1, 48), (0, 4, 32)]
 for var in variants:
     bulk, unroll, tile = var[:3]
-    tpc, chunk = (var[3], var[4]) if len(var) > 3 else (8, 512)
+    tpc, chunk = (var[3], var[4]) if len(var) > 3 else (8, 0)
     ctx.set_option("permute_tpc", tpc)
     ctx.set_option("permute_chunk_below", chunk)
     ctx.set_option("permute_bulk", bulk)
@@ -58,7 +58,7 @@ for var in variants:
             best = min(best, e0.elapsed_time(e1))
         print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
 ctx.set_option("permute_tpc", 8)
-ctx.set_option("permute_chunk_below", 512)
+ctx.set_option("permute_chunk_below", 0)
 ctx.set_option("permute_bulk", 1)
 ctx.set_option("permute_unroll", 4)
 ctx.set_option("permute_tile", 96)

@@ -15,7 +15,8 @@ import torch  # noqa: E402
 import tnrkit.jl_b200 as tk  # noqa: E402
 
 scheme, chi, warm = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-model = sys.argv[4] if len(sys.argv) > 4 else "ising"
+model = sys.argv[4] if len(sys.argv) > 4 and "=" not in sys.argv[4] else "ising"
+opts = [a for a in sys.argv[4:] if "=" in a]          # engine options, e.g. disable_qr=1
 T = {"ising": lambda: tk.classical_ising(tk.Trivial), "ising_z2": lambda: tk.classical_ising(),
      "potts_z3": lambda: tk.classical_potts(3),
      "ising3d": lambda: tk.classical_ising_3D(tk.Trivial)}[model]()
@@ -23,6 +24,9 @@ kw = {"shard": False} if scheme == "HOTRG_3D" else {}
 s = getattr(tk, scheme)(T, **kw)
 trunc = tk.truncrank(chi)
 ctx = tk.default_context()
+for o in opts:
+    k, v = o.split("=")
+    ctx.set_option(k, int(v))
 s.finalize()
 for _ in range(warm):
     s.step(trunc)
@@ -40,4 +44,4 @@ torch.cuda.profiler.stop()
 c = ctx.counters()
 print(f"{scheme} {model} chi={chi}: step {warm + 1} took {e0.elapsed_time(e1) / 1e3:.3f} s "
       f"(norm {n:.12e}); launches {c['launches']}, GEMM launches {c['gemm_launches']}, "
-      f"GEMM flop {c['gemm_flops']:.3e}, dims {getattr(s.T, 'dims', None)}")
+      f"GEMM flop {c['gemm_flops']:.3e}, dims {getattr(s.T, 'dims', None)} options {opts}")
