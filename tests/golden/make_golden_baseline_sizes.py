@@ -86,7 +86,12 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    want = sys.argv[1:] or list(CASES)
+    argv = sys.argv[1:]
+    if "--out" in argv:          # separate output file (merge by hand): parallel generation
+        i = argv.index("--out")
+        PATH = argv[i + 1]
+        del argv[i:i + 2]
+    want = argv or list(CASES)
     out = {}
     if os.path.exists(PATH):
         with open(PATH) as f:

@@ -66,16 +66,28 @@ def test_block_sparse_chi128_configs2(tk, ctx, name, scheme, model):
     assert ctx.counters()["grouped_gemm_launches"] > before      # one grouped launch per contraction
     assert tuple(s.T.dims) == tuple(g["dims"]) == (128, 128, 128, 128)
     _cmp_norms(got, g)
-    # retained spectra of the two truncated SVDs of the last step, sector by sector
+    # retained spectra of the two truncated SVDs of the last step, sector by sector.  The
+    # coarse-grained tensors are numerically rank deficient (fewer than 128 singular values
+    # above rounding), and the order of rounding-level values is arbitrary in ANY implementation,
+    # so the comparison is on the values above NOISE * sigma_1: same sectors, same multiplicity
+    # per sector, same values to 1e-10 sigma_1; whatever else fills the 128 slots must be noise.
+    NOISE = 1e-12
     spectra = symmetric.LAST_SPECTRA[scheme.lower()]
     assert len(spectra) == len(g["spectra"]) == 2
     for S_gpu, sp_ref in zip(spectra, g["spectra"]):
-        assert sorted(S_gpu) == [c for c, _ in sp_ref]                 # same sectors kept
         top = max(max(v) for _, v in sp_ref)
-        for c, vals in sp_ref:
-            got_c = S_gpu[c].to_numpy()
-            assert got_c.shape == (len(vals),)                         # same multiplicity per sector
-            assert np.abs(got_c - np.array(vals)).max() <= RTOL * top
+        ref_sig = {c: np.array([x for x in vals if x > NOISE * top]) for c, vals in sp_ref}
+        assert sum(len(v) for v in ref_sig.values()) >= 16          # the case is not vacuous
+        kept = 0
+        for c in set(ref_sig) | set(S_gpu):
+            got_c = np.sort(S_gpu[c].to_numpy())[::-1] if c in S_gpu else np.zeros(0)
+            want = ref_sig.get(c, np.zeros(0))
+            sig = got_c[got_c > NOISE * top]
+            assert sig.shape == want.shape, (c, sig.shape, want.shape)   # multiplicity per sector
+            if len(want):
+                assert np.abs(sig - want).max() <= RTOL * top
+            kept += len(got_c)
+        assert kept == g["chi"]                                          # sector-global truncrank
 
 
 @pytest.mark.parametrize("name,scheme", [

@@ -171,6 +171,11 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
         else if (std::strcmp(key, "disable_qr") == 0) ctx->c.disable_qr = value != 0;
+        else if (std::strcmp(key, "jacobi_max_sweeps") == 0) {
+            TNR_CHECK(value >= 1 && value <= 1000, "jacobi_max_sweeps: 1..1000");
+            ctx->c.jacobi_max_sweeps = (int)value;
+        }
+        else if (std::strcmp(key, "disable_persistent_jacobi") == 0) ctx->c.disable_persistent_jacobi = value != 0;
         else throw Error(1, std::string("unknown option: ") + key);
     });
 }
@@ -712,7 +717,9 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "preconditioned_jacobi") *value = (double)c.preconditioned_jacobi;
         else if (n == "subspace_eigh") *value = (double)c.subspace_eigh;
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;
+        else if (n == "persistent_jacobi") *value = (double)c.persistent_jacobi;
         else if (n == "qr_factorizations") *value = (double)c.qr_factorizations;
+        else if (n == "jacobi_limit_accepted") *value = (double)c.jacobi_limit_accepted;
         else if (n == "jacobi_not_converged") *value = (double)c.jacobi_not_converged;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;
         else if (n == "gemm_flops") *value = c.gemm_flops;

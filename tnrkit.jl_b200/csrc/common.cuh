@@ -43,7 +43,9 @@ struct Counters {
     unsigned long long preconditioned_jacobi = 0;  // tall Jacobi problems preconditioned by Gram eigenvectors
     unsigned long long subspace_eigh = 0;       // eigh_trunc calls served by the subspace solver
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
+    unsigned long long persistent_jacobi = 0;    // Jacobi iterations run as one cooperative launch
     unsigned long long qr_factorizations = 0;    // blocked Householder QR factorizations (qr.cu)
+    unsigned long long jacobi_limit_accepted = 0; // sweep limit reached with only rounding-level rotations left
     unsigned long long jacobi_not_converged = 0; // one-sided Jacobi runs that hit the sweep limit (an error is raised)
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi
     double gemm_flops = 0.0;               // 2*m*n*k summed over GEMM launches
@@ -69,6 +71,8 @@ struct Context {
     int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)
     int ozaki_slices = 0;  // > 0: INT8 Ozaki engine for the big TN contractions (opt-in)
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
+    int jacobi_max_sweeps = 40;  // a Jacobi iteration that needs more raises an error
+    bool disable_persistent_jacobi = false;  // one launch per Jacobi round + host sync per sweep (round 1)
     bool disable_qr = false;  // tall problems: Gram-preconditioned Jacobi (round 1) instead of Householder QR + Jacobi of R
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
@@ -188,7 +192,10 @@ void fill_zero(Context* ctx, double* A, long long n);
 void fill_random(Context* ctx, double* x, long long n, unsigned long long seed);
 void axpy(Context* ctx, double* y, const double* x, double alpha, long long n);  // y += alpha x
 void sum_squares(Context* ctx, const double* x, long long n, double* dev_out);   // deterministic
-void sqrt_inplace(Context* ctx, const double* dev_in, double* dev_out);          // *out = sqrt(max(*in, 0))
+void sqrt_inplace(Context* ctx, const double* dev_in, double* dev_out);
+// A (m x n, lda): column j <- 0 where |vals[j]| <= rel * |vals[0]| (vals sorted by magnitude)
+void zero_small_columns(Context* ctx, double* A, long long m, long long n, long long lda,
+                        const double* vals, double rel);          // *out = sqrt(max(*in, 0))
 // dot of two strided "vectors" with weights: out = |sum_{i,j..}|, used by BTRG finalize
 // dst = flag ? a : b, flag = (*epsA > *epsB)  (device side choice, HOTRG projector pick)
 void select_copy(Context* ctx, double* dst, const double* a, const double* b, long long n,

@@ -183,6 +183,24 @@ void fill_zero(Context* ctx, double* A, long long n) {
     TNR_CUDA(cudaMemsetAsync(A, 0, n * sizeof(double), ctx->stream));
 }
 
+__global__ void zero_small_columns_kernel(double* A, long long m, long long lda,
+                                          const double* __restrict__ vals, double rel) {
+    const int j = blockIdx.y;
+    if (!(fabs(vals[j]) <= rel * fabs(vals[0]))) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m;
+         i += (long long)gridDim.x * blockDim.x)
+        A[(long long)j * lda + i] = 0.0;
+}
+
+void zero_small_columns(Context* ctx, double* A, long long m, long long n, long long lda,
+                        const double* vals, double rel) {
+    if (m <= 0 || n <= 0) return;
+    dim3 grid((unsigned)std::min<long long>((m + 255) / 256, 64), (unsigned)n);
+    zero_small_columns_kernel<<<grid, 256, 0, ctx->stream>>>(A, m, lda, vals, rel);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
 __global__ void sqrt_scalar_kernel(const double* in, double* out) { *out = sqrt(fmax(*in, 0.0)); }
 
 void sqrt_inplace(Context* ctx, const double* dev_in, double* dev_out) {

@@ -116,12 +116,18 @@ struct BulkIssue {
             : "memory");
     }
 };
+// explicit st.global: the destination pointer travels through shared memory (tile geometry), so
+// the compiler would otherwise fall back to generic-space stores
 struct Store1 {
-    __device__ __forceinline__ void operator()(double* g, const double* t) const { *g = *t; }
+    __device__ __forceinline__ void operator()(double* g, const double* t) const {
+        const double v = *t;
+        asm volatile("st.global.f64 [%0], %1;\n" ::"l"(g), "d"(v) : "memory");
+    }
 };
 struct Store2 {
     __device__ __forceinline__ void operator()(double* g, const double* t) const {
-        *reinterpret_cast<double2*>(g) = *reinterpret_cast<const double2*>(t);
+        const double2 v = *reinterpret_cast<const double2*>(t);
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};\n" ::"l"(g), "d"(v.x), "d"(v.y) : "memory");
     }
 };
 

@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "tensor.hpp"
 
 namespace tnr {
@@ -320,6 +323,12 @@ DT gram_orthonormalize(Context* ctx, const DT& Y, long long n, long long b) {
     return Q;
 }
 
+static bool trace_on() {
+    static int v = -1;
+    if (v < 0) v = std::getenv("TNR_TRACE") ? 1 : 0;
+    return v == 1;
+}
+
 bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out) {
     long long b = std::min(n, std::max(2 * k, k + 64));
     b += (b & 1);
@@ -345,6 +354,9 @@ bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out)
         DT QSn(ctx, {n, b}), ZS(ctx, {n, b});
         gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Q.p, n, e.U.p, b, 0.0, QSn.p, n);
         gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Z.p, n, e.U.p, b, 0.0, ZS.p, n);
+        // Ritz pairs below 1e-14 |theta|_max: numerically null directions, returned as zeros
+        zero_small_columns(ctx, QSn.p, n, b, n, e.S.p, 1e-14);
+        zero_small_columns(ctx, ZS.p, n, b, n, e.S.p, 1e-14);
         Z.release();
         // residuals of the kept pairs: R = MM x - theta x = ZS[:, :k] - QS[:, :k] diag(theta)
         DT R(ctx, {n, k});
@@ -360,6 +372,7 @@ bool eigh_topk(Context* ctx, const DT& MM, long long n, long long k, Trunc& out)
         double tmax = std::fabs(theta[0]), res = 0.0;
         for (long long j = 0; j < k; ++j) res = std::max(res, rn[j]);
         res = (tmax > 0.0) ? res / tmax : 0.0;
+        if (trace_on()) fprintf(stderr, "[eigh_topk n=%lld k=%lld b=%lld] it %d res %.3e theta0 %.3e theta_k %.3e\n", n, k, b, it, res, theta[0], theta[k - 1]);
         if (!std::isfinite(res)) return false;
         QS = std::move(QSn);
         Th = std::move(e.S);
@@ -467,6 +480,11 @@ bool svd_topk(Context* ctx, const DT& T, long long m, long long n, long long k, 
         DT Un(ctx, {m, b}), Wg(ctx, {b, b}), Xn(ctx, {n, b});
         gather_columns(ctx, Y.p, m, b, m, rank.p, b, Un.p, m, vals.p, true);   // unit left vectors
         gather_columns(ctx, W.p, b, b, b, rank.p, b, Wg.p, b, nullptr, false);
+        // triplets below 1e-14 sigma_1 are rounding noise of a numerically rank-deficient operator:
+        // their left vectors are returned as ZEROS (they enter later contractions with weight
+        // sigma or sqrt(sigma)); a Householder-orthonormalised basis would otherwise carry
+        // arbitrary unit vectors there, whose residuals never certify
+        zero_small_columns(ctx, Un.p, m, b, m, Sn.p, 1e-14);
         Y.release();
         gemm(ctx, 'N', 'N', (int)n, (int)b, (int)b, 1.0, Q.p, n, Wg.p, b, 0.0, Xn.p, n);  // right
         DT Z(ctx, {n, b});
@@ -484,6 +502,7 @@ bool svd_topk(Context* ctx, const DT& T, long long m, long long n, long long k, 
         double smax = sig[0], res = 0.0;
         for (long long j = 0; j < k; ++j) res = std::max(res, rn[j]);
         res = (smax > 0.0) ? res / smax : 0.0;
+        if (trace_on()) fprintf(stderr, "[svd_topk %lldx%lld k=%lld b=%lld] it %d res %.3e s0 %.3e s_k %.3e s_b %.3e\n", m, n, k, b, it, res, sig[0], sig[k - 1], sig[b - 1]);
         if (!std::isfinite(res)) return false;
         Us = std::move(Un);
         X = std::move(Xn);
