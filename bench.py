@@ -22,10 +22,12 @@ ranks.  Inputs (1.5 GB at chi=24) exceed the 126 MB L2, so no explicit flush is 
 Time box.  One steady-state chi=24 step is 9.15e15 FP64 flop, i.e. >= 229 s at the nominal
 40 TFLOP/s of the chip, so `--steps 20 --warmup 5` cannot fit any driver limit at N=1.  The run
 therefore has a wall budget (`--time-budget`, default 780 s counted from interpreter start;
-0 disables it): warm-up stops as soon as >= 3 iterations ran AND every leg equals chi (RG
-iteration 3) when the requested count would overrun; timed steps run until the next one would
+0 disables it): warm-up stops as soon as >= 2 iterations ran AND every leg equals chi (RG
+iteration 2) when one more warm-up plus two timed steps would overrun; timed steps run until the next one would
 overrun, never fewer than min(2, K).  The JSON line reports the steps and warm-ups actually
 done (`steps`, `warmup`) and what was asked for (`steps_requested`, `warmup_requested`).
+(The legs are saturated after RG iteration 2; iteration 3 is already a full-cost step, so on one
+GPU the default budget leaves room for 2 warm-up iterations + 2 timed steps.)
 """
 from __future__ import annotations
 
@@ -363,22 +365,35 @@ def run_gpu(args):
         return all(d == chi for d in state_dims())
 
     # ---- warm-up: RG iterations 1..W (untimed) -------------------------------------------
+    # Bond dimensions grow 2 -> 16 -> chi: every leg equals chi after RG iteration 2, and
+    # iteration 3 already costs a full steady-state step (260 s at chi = 24 on one GPU).  When the
+    # requested schedule cannot fit the budget, warm-up ends as soon as the legs are saturated
+    # (>= 2 iterations: all kernels of the step have run at nearly full size) and one more
+    # warm-up plus the minimum of two timed steps would overrun.
     w_done = 0
     last = 0.0
+    est_full = 0.0
+    min_steps = min(2, args.steps)
+    full_flop_rank = (step_flops(chi) / world) if not atrg else None
     while w_done < args.warmup:
-        if budget > 0 and w_done >= 3 and saturated():
-            elapsed, last_ = agree(time.time() - T_START, last)
-            if elapsed + (args.warmup - w_done + args.steps) * last_ > budget:
+        if budget > 0 and w_done >= 2 and saturated():
+            elapsed, est_ = agree(time.time() - T_START, est_full)
+            if elapsed + (1 + min_steps) * est_ > budget:
                 break
+        f0 = ctx.counters()["gemm_flops"]
         t0 = time.perf_counter()
         scheme.step(trunc)
         norms.append(scheme.finalize())
         torch.cuda.synchronize()
         last = time.perf_counter() - t0
+        flop_it = ctx.counters()["gemm_flops"] - f0
+        # a full steady-state step, extrapolated by flops from this (smaller) iteration
+        est_full = last * max(1.0, (full_flop_rank / flop_it) if (full_flop_rank and flop_it > 0)
+                              else 1.0)
         w_done += 1
         if rank == 0:
             log(f"warm-up step {w_done}/{args.warmup}: dims {state_dims()} norm "
-                f"{norms[-1]:.6e} {last:.1f}s (t+{time.time() - T_START:.0f}s)")
+                f"{norms[-1]:.6e} {last:.1f}s, full step ~{est_full:.0f}s (t+{time.time() - T_START:.0f}s)")
     if rank == 0 and not saturated():
         log(f"WARNING: bond dimensions not yet saturated after warm-up: {state_dims()}")
 
@@ -395,9 +410,8 @@ def run_gpu(args):
         sampler.start()
     wall0 = time.perf_counter()
     h2d = d2h = 0
-    est = 0.0
+    est = est_full
     k_done = 0
-    min_steps = min(2, args.steps)
     first_iter = w_done + 1
     for s in range(args.steps):
         if budget > 0 and s >= min_steps:
@@ -488,7 +502,7 @@ def run_gpu(args):
                 "time_budget_s": budget,
                 "time_box": (f"{K} of {args.steps} requested timed steps and {w_done} of "
                              f"{args.warmup} requested warm-up iterations fit the wall budget; "
-                             "all legs equal chi from RG iteration 3 on, so every timed step is "
+                             "all legs equal chi from RG iteration 2 on, so every timed step is "
                              "a steady-state step") if (K < args.steps or w_done < args.warmup)
                 else "all requested steps ran",
                 "parallelism": "1 GPU" if world == 1 else

@@ -105,3 +105,63 @@ def test_hotrg3d_sharded_two_gpus():
     assert res[0]["nccl"] == res[1]["nccl"]  # replicas stay bit-identical
     print("peer-scatter launches per rank:", res[0]["peers_peer_launches"],
           "(0 means symmetric memory was unavailable and the NCCL path was used)")
+
+
+def _sweep_worker(rank, world, port, betas, chi, nsteps, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    import tnrkit.jl_b200 as tk
+
+    ctx = tk.default_context()
+    ctx.reset_counters()
+    res2d = tk.beta_sweep(tk.TRG, lambda b: tk.classical_ising(tk.Trivial, b), betas,
+                          tk.truncrank(chi), tk.maxiter(nsteps))
+    n2d = ctx.counters()["launches"]
+    res3d = tk.beta_sweep(tk.HOTRG_3D, lambda b: tk.classical_ising_3D(tk.Trivial, b), betas[:2],
+                          tk.truncrank(4), tk.maxiter(2))
+    q.put((rank, res2d, res3d, n2d))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_beta_sweep_two_gpus():
+    """beta-sweep on 2 processes / 2 GPUs (north star: one independent scheme per GPU, no
+    collective on the data path): rank r runs betas[r::2], the norm lists are exchanged as host
+    objects at the end, every rank holds all of them and each equals the oracle at its beta."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tnr_oracle as o
+
+    betas = [0.40, 0.42, 0.44068679350977147, 0.46, 0.48]
+    chi, nsteps = 8, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, betas, chi, nsteps, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (a, b, n) for r, a, b, n in (q.get(timeout=300) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]     # everybody holds every result
+    assert res[0][2] > 0 and res[1][2] > 0                       # both GPUs did device work
+    assert res[0][2] > res[1][2]                                 # rank 0 ran 3 of the 5 betas
+    for b, got in zip(betas, res[0][0]):
+        ref = np.array(o.run(o.TRG(o.classical_ising(b)), chi, nsteps))
+        assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, b
+    for b, got in zip(betas[:2], res[0][1]):
+        ref = np.array(o.run(o.HOTRG_3D(o.classical_ising_3D(b)), 4, 2))
+        assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, b
