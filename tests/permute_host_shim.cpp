@@ -41,9 +41,20 @@ static int run_bulk(const double* src, double* dst, const BulkPlan& bp, long lon
             double* tb = tile_buf + t * tile_elems;
             for (int tid = 0; tid < 256; ++tid) {
                 if (p.chunked) bulk_load_phase_chunked(g, p, tb, tid, 256, issue16);
+                else if (p.dense) bulk_load_phase_dense(g, p, tb, tid, 256, issue);
                 else bulk_load_phase(g, p, tb, tid, 256, issue);
             }
             if (bytes != bulk_tile_bytes(g)) ++bad;      // the mbarrier's expect_tx count
+            if (p.dense) {   // re-pitch: all threads load (phase 0), barrier, all threads store
+                std::vector<BulkD2> regs(256 * BULK_REPITCH);
+                for (int ph = 0; ph < 2; ++ph)
+                    for (int tid = 0; tid < 256; ++tid) {
+                        BulkD2(&rg)[BULK_REPITCH] =
+                            *reinterpret_cast<BulkD2(*)[BULK_REPITCH]>(&regs[tid * BULK_REPITCH]);
+                        bulk_repitch(g, p, tb, tid, 256, rg, ph);
+                    }
+                info[5] = 100 + p.vec;   // tells the test that the dense path ran
+            }
         }
         for (int t = 0; t < nt; ++t) {
             BulkGeom g = bulk_geometry(src, dst, p, t0 + t);

@@ -63,6 +63,9 @@ BULK_CASES = [
     ((2, 9, 9), (0, 2, 1)), ((6, 10, 14), (2, 1, 0)), ((48,) * 4, (3, 1, 2, 0)),
     ((48,) * 4, (0, 3, 2, 1)), ((20, 30, 40), (1, 2, 0)), ((1728, 1730), (1, 0)),
     ((7, 4, 6), (0, 2, 1)),
+    # short source rows fetched densely and re-pitched in shared memory
+    ((24, 24, 6, 4), (1, 0, 2, 3)), ((24, 200), (1, 0)), ((8, 30, 6), (1, 0, 2)), ((16, 98), (1, 0)),
+    ((62, 40), (1, 0)), ((24,) * 4, (1, 3, 0, 2)),
 ]
 
 

@@ -247,3 +247,21 @@ def test_bulk_kernel_fuzz(shim):
         assert np.array_equal(np.isnan(got), np.isnan(want)), (big_s, dims, big_d_perm, kind)
         assert np.array_equal(got[sl_d], want[sl_d]), (big_s, dims, big_d_perm, kind)
     assert took >= 40, took
+
+
+def test_bulk_dense_repitch_path_is_taken(shim):
+    """Short source rows that follow each other contiguously (2-D transposition with a short
+    source-contiguous leg: `Qn -> Qk` and the Gram operand of the HOTRG_3D step): ONE bulk piece
+    per j2 slice, re-pitched in shared memory.  info[5] >= 100 marks the dense path."""
+    rng = np.random.default_rng(21)
+    for dims, perm in [((12,) * 6, (1, 3, 5, 0, 2, 4)), ((12,) * 6, (1, 2, 3, 4, 0, 5)),
+                       ((24, 24, 6, 4), (1, 0, 2, 3)), ((24, 200), (1, 0)), ((8, 30, 6), (1, 0, 2)),
+                       ((16, 98), (1, 0)), ((62, 40), (1, 0))]:
+        a = rng.standard_normal(dims)
+        kind, got, info = _run(shim, a, perm, -1, 96)
+        assert kind == 4 and info[5] >= 100, (dims, perm, kind, info)
+        assert np.array_equal(got, np.transpose(a, perm))
+    # long rows keep one piece per row
+    a = rng.standard_normal((96, 200))
+    kind, got, info = _run(shim, a, (1, 0), -1, 96)
+    assert kind == 4 and info[5] < 100 and np.array_equal(got, a.T)

@@ -159,6 +159,7 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
             TNR_CHECK(value >= 1, "hotrg3d_pk_budget_mb: megabytes of absorbed operands held at once");
             ctx->c.hotrg3d_pk_budget = (long long)value << 20;
         }
+        else if (std::strcmp(key, "permute_dense") == 0) ctx->c.permute_dense = value != 0;
         else if (std::strcmp(key, "permute_tpc") == 0) {
             TNR_CHECK(value >= 1 && value <= 8, "permute_tpc: 1..8");
             ctx->c.permute_tpc = (int)value;

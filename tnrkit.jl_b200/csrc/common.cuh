@@ -66,6 +66,7 @@ struct Context {
     int permute_tile = 96;   // composite run length of the tiled permute kernel (opt-in: 32 | 48 | 64)
     int permute_unroll = 4;  // 1 | 2 | 4: rows of the read phase in flight per thread in the fallback tiled kernel (r02: 4 measured 1.7x faster than 1)
     int permute_tpc = 8;       // max tiles per CTA of the TMA-fed copy (tuning)
+    bool permute_dense = true;  // dense fetch + in-place re-pitch of short contiguous source rows
     int permute_chunk_below = 0;  // rows below this many bytes: cp.async chunks instead of bulk pieces (tuning)
     bool permute_bulk = true;  // TMA-fed tiled copy (cp.async.bulk) whenever the source pieces are 16-byte aligned
     int ozaki_crt = 0;     // 14..18: CRT variant of the INT8 engine with that many moduli (opt-in, unmeasured)

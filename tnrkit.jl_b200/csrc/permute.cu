@@ -139,7 +139,7 @@ struct Issue16 {
 };
 
 template <int VEC>
-__global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict__ src,
+__global__ void __launch_bounds__(256, 3) copy_bulk_kernel(const double* __restrict__ src,
                                                         double* __restrict__ dst,
                                                         const BulkParams p) {
     extern __shared__ __align__(16) double dyn_smem[];
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict
             if (threadIdx.x == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
                              ::"r"(bar), "r"((int)bulk_tile_bytes(g)) : "memory");
-            bulk_load_phase(g, p, tile + t * tile_elems, threadIdx.x, 256, BulkIssue{bar});
+            if (p.dense) bulk_load_phase_dense(g, p, tile + t * tile_elems, threadIdx.x, 256, BulkIssue{bar});
+            else bulk_load_phase(g, p, tile + t * tile_elems, threadIdx.x, 256, BulkIssue{bar});
         } else {
             bulk_load_phase_chunked(g, p, tile + t * tile_elems, threadIdx.x, 256, Issue16{});
         }
@@ -202,6 +203,13 @@ __global__ void __launch_bounds__(256) copy_bulk_kernel(const double* __restrict
                 "}\n" ::"r"(bsmem_u32(&bar_storage[t])), "r"(0) : "memory");
         }
         const BulkGeom g = sgeom[t];
+        if (p.dense) {
+            BulkD2 regs[BULK_REPITCH];
+            bulk_repitch(g, p, tile + t * tile_elems, threadIdx.x, 256, regs, 0);
+            __syncthreads();
+            bulk_repitch(g, p, tile + t * tile_elems, threadIdx.x, 256, regs, 1);
+            __syncthreads();
+        }
         const bool full = g.tv == p.TV && g.tj1 == p.TJ1 && g.cj == p.TJ1 * p.TJ2;
         if (full) {
             if (VEC == 2) bulk_write_phase<2>(g, p, tile + t * tile_elems, warp, full_tab, Store2{});
@@ -301,6 +309,7 @@ void strided_copy(Context* ctx, const double* src, double* dst, int rank, const 
         BulkTuning tune;
         tune.max_tpc = ctx->permute_tpc;
         tune.chunk_below = ctx->permute_chunk_below;
+        tune.dense = ctx->permute_dense ? 1 : 0;
         BulkPlan bp = plan_bulk_copy(merged_groups(rank, dims, sstride, dstride), (uintptr_t)src,
                                      (uintptr_t)dst, ctx->permute_tile, tune);
         if (bp.ok) {

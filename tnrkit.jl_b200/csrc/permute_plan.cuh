@@ -198,6 +198,8 @@ inline std::vector<BulkGroup> merged_groups(int rank, const long long* dims,
 constexpr int BULK_KMAX = 6;          // elements (of VEC doubles) per lane and output run
 constexpr int BULK_TILE_ELEMS = 9216; // doubles per tile (72 KB): 3 CTAs per SM
 constexpr int BULK_MAX_TPC = 8;       // tiles per CTA
+constexpr int BULK_REPITCH = 5;       // double2 per thread held while a dense tile is re-pitched
+constexpr int BULK_DENSE_ELEMS = BULK_REPITCH * 256 * 2;   // doubles per dense tile
 
 struct BulkLaneTab {
     int so[BULK_KMAX];        // shared-memory offset of the slot (doubles), -1 = unused
@@ -220,6 +222,8 @@ struct BulkParams {
     int tpc;                // tiles per CTA (small tiles: several in flight per CTA)
     int chunked;            // 1: rows shorter than 512 B are fetched as 16-byte cp.async chunks
     int tab_smem;           // 1: the lane table is computed by one warp and shared (small tiles)
+    int dense;              // 1: short source rows that follow each other contiguously are fetched
+                            //    as ONE piece per j2 slice and re-pitched in shared memory
     long long ntiles;       // total number of tiles (grid = ceil(ntiles / tpc))
 };
 
@@ -243,6 +247,7 @@ inline int bulk_pick_extent(long long n, long long tgt, bool want_even) {
 // the copy does not have the structure / alignment the bulk kernel needs.
 struct BulkTuning {
     int max_tpc = BULK_MAX_TPC;     // tiles per CTA (1 = one tile per CTA)
+    int dense = 1;                  // dense fetch + re-pitch of short contiguous rows
     int chunk_below = 0;            // whole-row pieces below this many bytes use cp.async chunks
     //                                 (0 = never: measured equal to bulk pieces, more instructions)
 };
@@ -381,6 +386,11 @@ inline BulkPlan plan_bulk_copy(const std::vector<BulkGroup>& m, uintptr_t src_ad
     // whole-row pieces below 512 bytes go through 16-byte cp.async chunks instead of one bulk
     // request per piece
     p.chunked = (p.contig2 && row * 8 < tune.chunk_below) ? 1 : 0;
+    // rows of less than 512 bytes that follow each other contiguously in the source (j1 continues
+    // the row: a 2-D transposition with a short source-contiguous leg): one bulk request per j2
+    // slice instead of one per 192-byte row, then an in-place re-pitch through registers
+    p.dense = (tune.dense && !p.chunked && p.contig2 && row * 8 < 512 && p.s_j1 == row &&
+               (long long)p.TJ1 * p.TJ2 * row <= BULK_DENSE_ELEMS) ? 1 : 0;
     out.smem = tile_smem * (size_t)tpc + (p.tab_smem ? sizeof(BulkLaneTab) * 32 : 0);
     out.blocks = (p.ntiles + tpc - 1) / tpc;
     out.ok = true;
@@ -477,6 +487,36 @@ TNR_HD void bulk_load_phase(const BulkGeom& g, const BulkParams& p, double* tile
                            (long long)a1 * p.s_i1 + (long long)a2 * p.s_i2;
         double* tp = tile + (long long)r * p.pitch + (int)((a2 * (unsigned)g.ti1 + a1) * (unsigned)g.tv);
         issue(tp, sp, plen * 8);
+    }
+}
+
+// dense tiles: one piece per j2 slice (tj1 consecutive rows are contiguous in the source),
+// landing densely at the start of the tile buffer
+template <typename Issue>
+TNR_HD void bulk_load_phase_dense(const BulkGeom& g, const BulkParams& p, double* tile, int tid,
+                                  int nthreads, Issue issue) {
+    const int row = g.ci * g.tv;
+    for (int j2 = tid; j2 < g.tj2; j2 += nthreads)
+        issue(tile + (long long)j2 * g.tj1 * row, g.sp + (long long)j2 * p.s_j2, g.tj1 * row * 8);
+}
+
+// in-place re-pitch of a dense tile (rows of `row` doubles back to back) to the padded pitch:
+// every thread first takes its 16-byte units into registers (phase 0), then -- after a CTA
+// barrier -- writes them to their padded position (phase 1)
+struct BulkD2 { double x, y; };
+TNR_HD void bulk_repitch(const BulkGeom& g, const BulkParams& p, double* tile, int tid,
+                         int nthreads, BulkD2 (&regs)[BULK_REPITCH], int phase) {
+    const unsigned row2 = (unsigned)(g.ci * g.tv) / 2, n2 = (unsigned)g.cj * row2;
+    BulkD2* t2 = reinterpret_cast<BulkD2*>(tile);
+#pragma unroll
+    for (int k = 0; k < BULK_REPITCH; ++k) {
+        const unsigned idx = (unsigned)tid + (unsigned)nthreads * k;
+        if (idx >= n2) continue;
+        if (phase == 0) regs[k] = t2[idx];
+        else {
+            const unsigned r = idx / row2, o = idx - r * row2;
+            t2[r * (unsigned)(p.pitch / 2) + o] = regs[k];
+        }
     }
 }
 

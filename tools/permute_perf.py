@@ -18,19 +18,21 @@ cases = [("rotate ((6,4),(2,3,1,5))", (chi,) * 6, (5, 3, 1, 2, 0, 4)),
          ("tall transpose chi^4 x chi^2", (chi ** 4, chi ** 2), (1, 0)),
          ("ATRG_3D ((4,1),(2,3))-like", (chi,) * 6, (3, 0, 1, 2, 5, 4)),
          ("flat copy", (chi ** 6,), (0,))]
-# (bulk, unroll, tile[, tpc, chunk_below])
-variants = [(1, 4, 96, 8, 0), (1, 4, 96, 8, 512), (1, 4, 96, 1, 0), (0, 4, 96)] if len(sys.argv) < 3 else \
+# (bulk, unroll, tile[, tpc, chunk_below, dense])
+variants = [(1, 4, 96, 8, 0, 1), (1, 4, 96, 8, 0, 0), (1, 4, 96, 1, 0, 1), (0, 4, 96)] if len(sys.argv) < 3 else \
     [(0, 1, 96), (0, 2, 96), (0, 4, 96), (0, 4, 64), (0, 4, 48), (0, 1, 48), (0, 4, 32)]
 for var in variants:
     bulk, unroll, tile = var[:3]
     tpc, chunk = (var[3], var[4]) if len(var) > 3 else (8, 0)
+    dense = var[5] if len(var) > 5 else 1
+    ctx.set_option("permute_dense", dense)
     ctx.set_option("permute_tpc", tpc)
     ctx.set_option("permute_chunk_below", chunk)
     ctx.set_option("permute_bulk", bulk)
     ctx.set_option("permute_unroll", unroll)
     ctx.set_option("permute_tile", tile)
     print(f"--- permute_bulk = {bulk}, permute_unroll = {unroll}, permute_tile = {tile}, "
-          f"permute_tpc = {tpc}, permute_chunk_below = {chunk}", flush=True)
+          f"permute_tpc = {tpc}, permute_chunk_below = {chunk}, permute_dense = {dense}", flush=True)
     for name, dims, perm in cases:
         n = 1
         for d in dims: n *= d
@@ -57,6 +59,7 @@ for var in variants:
             e0.record(); run(); e1.record(); e1.synchronize()
             best = min(best, e0.elapsed_time(e1))
         print(f"{name:28s} {n*8/1e9:6.2f} GB  {best:8.3f} ms  {16.0*n/(best*1e-3)/1e9:8.1f} GB/s (read+write)", flush=True)
+ctx.set_option("permute_dense", 1)
 ctx.set_option("permute_tpc", 8)
 ctx.set_option("permute_chunk_below", 0)
 ctx.set_option("permute_bulk", 1)
