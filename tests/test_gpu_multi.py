@@ -107,6 +107,9 @@ def test_hotrg3d_sharded_two_gpus():
           "(0 means symmetric memory was unavailable and the NCCL path was used)")
 
 
+BETAS_3D = [0.20, 0.2216544, 0.25]
+
+
 def _sweep_worker(rank, world, port, betas, chi, nsteps, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -124,7 +127,9 @@ def _sweep_worker(rank, world, port, betas, chi, nsteps, q):
     res2d = tk.beta_sweep(tk.TRG, lambda b: tk.classical_ising(tk.Trivial, b), betas,
                           tk.truncrank(chi), tk.maxiter(nsteps))
     n2d = ctx.counters()["launches"]
-    res3d = tk.beta_sweep(tk.HOTRG_3D, lambda b: tk.classical_ising_3D(tk.Trivial, b), betas[:2],
+    # (3D Ising at beta = 0.40 is deep in the ordered phase: truncrank(4) cuts a degenerate
+    #  multiplet there and the oracle itself moves by 2e-5 under a 1e-14 perturbation)
+    res3d = tk.beta_sweep(tk.HOTRG_3D, lambda b: tk.classical_ising_3D(tk.Trivial, b), BETAS_3D,
                           tk.truncrank(4), tk.maxiter(2))
     q.put((rank, res2d, res3d, n2d))
     dist.barrier()
@@ -162,6 +167,9 @@ def test_beta_sweep_two_gpus():
     for b, got in zip(betas, res[0][0]):
         ref = np.array(o.run(o.TRG(o.classical_ising(b)), chi, nsteps))
         assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, b
-    for b, got in zip(betas[:2], res[0][1]):
-        ref = np.array(o.run(o.HOTRG_3D(o.classical_ising_3D(b)), 4, 2))
+    from conditioning import require_well_conditioned
+
+    for b, got in zip(BETAS_3D, res[0][1]):
+        ref = require_well_conditioned(lambda t: o.run(o.HOTRG_3D(t), 4, 2),
+                                       o.classical_ising_3D(b), f"HOTRG_3D beta={b}")
         assert np.max(np.abs(np.array(got) - ref) / np.abs(ref)) <= 1e-10, b
