@@ -595,7 +595,7 @@ def main():
     ap.add_argument("--workload", default="hotrg3d", choices=["hotrg3d", "atrg3d"],
                     help="hotrg3d: the headline (BASELINE.json metric, configs[4], chi=24); atrg3d: "
                          "configs[3] (use --chi 48), same time box and JSON contract")
-    ap.add_argument("--rfactor", default="tsqr", choices=["tsqr", "gram"])
+    ap.add_argument("--rfactor", default="tsqr", choices=["tsqr", "gram", "gram_eigh"])
     ap.add_argument("--factored", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--crt-moduli", type=int, default=16)

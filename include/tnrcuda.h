@@ -165,6 +165,14 @@ int tnr_qr(tnr_context* ctx, const double* A, int64_t m, int64_t n, double* Q, d
  * The isometry Q is never formed.  Used chunk by chunk (TSQR) by the factored ATRG_3D step. */
 int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims, int ncod,
                double* R);
+/* A factor L (n x n, column major; columns >= *rank_out are zero) with L L^T = G for a symmetric
+ * positive semidefinite G (n x n, not modified): diagonally pivoted Cholesky without row
+ * exchanges, stopped at the numerical rank (largest remaining diagonal entry <= 8 eps max_i G_ii).
+ * With G = A^T A, L^T is an R factor of A up to a left orthogonal gauge -- the only property of
+ * `_, R = left_orth(...)` / `R, _ = right_orth(...)` that src/schemes/atrg3d.jl:53-66 uses; the
+ * factored ATRG_3D step obtains its four R factors this way from the chi^2 x chi^2 Gram matrices of
+ * the matricizations of YD / AX (one launch per column + one DMMA GEMM per 64 columns). */
+int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int64_t* rank_out);
 /* eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) (src/schemes/hotrg.jl:106,114,
  * hotrg3d.jl:94-98).  Keeps the chi eigenvalues of largest magnitude.  MM is n x n and is
  * not modified.  W: k signed eigenvalues, V: n x k. */

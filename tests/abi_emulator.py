@@ -191,6 +191,40 @@ class EmulatedContext:
         assert m >= n, "orth_r: expects a tall matrix"
         _f(R, (n, n))[...] = np.linalg.qr(_f(T, (m, n)), mode="r")
 
+    PSD_REL = 8 * np.finfo(float).eps      # csrc/pchol.cu: PCHOL_REL
+
+    def _tnr_psd_factor(self, G, n, L, rank_out):
+        """The algorithm of csrc/pchol.cu restated column by column: diagonal pivoting WITHOUT
+        row exchanges (L is not triangular; only L L^T = G matters), stop when the largest
+        remaining diagonal entry is <= PSD_REL * max_i G[i, i], |L[i, j]| clamped to
+        sqrt(d[i]) (Cauchy-Schwarz of a PSD Schur complement) so that rounding noise can
+        never be amplified."""
+        n = int(n)
+        S = _f(G, (n, n))
+        S = 0.5 * (S + S.T)
+        Lm = np.zeros((n, n))
+        d = np.maximum(np.diag(S).copy(), 0.0)
+        thresh = self.PSD_REL * (d.max() if n else 0.0)
+        active = np.ones(n, dtype=bool)
+        r = 0
+        for j in range(n):
+            cand = np.where(active, d, -1.0)
+            p = int(np.argmax(cand))
+            if not cand[p] > thresh:
+                break
+            piv = np.sqrt(d[p])
+            col = (S[:, p] - Lm[:, :j] @ Lm[p, :j]) / piv
+            lim = np.sqrt(d)
+            col = np.clip(col, -lim, lim)
+            col[~active] = 0.0
+            col[p] = piv
+            Lm[:, j] = col
+            d = np.maximum(d - col * col, 0.0)
+            active[p] = False
+            r = j + 1
+        _f(L, (n, n))[...] = Lm
+        C.cast(rank_out, C.POINTER(C.c_int64))[0] = r
+
     def _tnr_eigh_trunc(self, MM, n, chi, W, V, k_out, eps_out):
         M = _f(MM, (n, n))
         w, v = np.linalg.eigh(0.5 * (M + M.T))

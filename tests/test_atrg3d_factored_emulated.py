@@ -176,18 +176,20 @@ def test_factored_atrg3d_matches_committed_golden_chi12(tk, emu):
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
 
 
-@pytest.mark.parametrize("chi,n", [(6, 4), (10, 3)])
-def test_factored_atrg3d_gram_r_factors_match_oracle(tk, emu, chi, n):
+@pytest.mark.parametrize("chi,n,rfactor", [(6, 4, "gram"), (10, 3, "gram"), (6, 4, "gram_eigh")])
+def test_factored_atrg3d_gram_r_factors_match_oracle(tk, emu, chi, n, rfactor):
     """rfactor="gram": R factors from the Gram matrices of the two-factor tensors (O(chi^6), no
-    chunk is ever formed for them) -- same norm lists as the oracle's Householder QR at 1e-10."""
+    chunk is ever formed for them; pivoted Cholesky `tnr_psd_factor`, or the eigendecomposition
+    with "gram_eigh") -- same norm lists as the oracle's Householder QR at 1e-10."""
     from tnrkit.jl_b200 import atrg3d_factored as af
 
     T = tk.classical_ising_3D(tk.Trivial)
-    s = tk.ATRG_3D(T, factored=True, rfactor="gram")
+    s = tk.ATRG_3D(T, factored=True, rfactor=rfactor)
     got = np.array(tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0))
     ref = np.array(o.run(o.ATRG_3D(T), chi, n))
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL
-    assert af.LAST_STATS["rfactor"] == "gram" and "tnr_orth_r" not in emu.calls
+    assert af.LAST_STATS["rfactor"] == rfactor and "tnr_orth_r" not in emu.calls
+    assert ("tnr_psd_factor" in emu.calls) == (rfactor == "gram")
     with pytest.raises(ValueError):
         tk.ATRG_3D(T, factored=True, rfactor="qr").step(tk.truncrank(4))
 

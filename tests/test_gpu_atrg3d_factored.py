@@ -82,7 +82,7 @@ def test_full_size_parity_dense_and_factored_device_steps(tk, ctx, chi):
     dense = np.array(tk.run(tk.ATRG_3D(T, factored=False), tk.truncrank(chi), tk.maxiter(3),
                             verbosity=0))
     assert np.max(np.abs(dense - ref) / np.abs(ref)) <= RTOL
-    for rfactor in ("tsqr", "gram"):
+    for rfactor in ("tsqr", "gram", "gram_eigh"):
         fact = np.array(tk.run(tk.ATRG_3D(T, factored=True, rfactor=rfactor), tk.truncrank(chi),
                                tk.maxiter(3), verbosity=0))
         assert np.max(np.abs(fact - ref) / np.abs(ref)) <= RTOL, rfactor

@@ -231,13 +231,16 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
         return dense_svd("block covers the matrix")
     rng = np.random.default_rng(seed)
     Q = DeviceTensor.from_numpy(rng.standard_normal(cd + (b,)), None, ctx)
+    ph = _Phases(ctx)
     Z = F.apply(rows, cols, Q)
+    ph.mark("apply")
     best, stalled = math.inf, 0
     Ul = sig = None
     eyes = {}
     for it in range(1, maxit + 1):
         U, S, _, _ = svd_trunc(_view(Z, (m, Z.dims[-1])), 1, NO_TRUNCATION)       # Z = U S W^T
         s = S.to_numpy()
+        ph.mark("svd_Z")
         keep = int(np.count_nonzero(s > 1e-14 * s[0]))
         if keep == 0:
             return dense_svd("zero operator")
@@ -246,11 +249,18 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
             eyes[ke] = DeviceTensor.from_numpy(np.eye(ke), None, ctx)
         U = DeviceTensor(U.buf[: m * keep], rd + (keep,), None, ctx)
         Y = F.apply(cols, rows, U)                                               # A^T U
+        ph.mark("apply")
         Vh, sig, Xt, _ = svd_trunc(_view(Y, (n, keep)), 1, NO_TRUNCATION)        # Y = Vh sig Xt
+        ph.mark("svd_Y")
         Ul = contract(_view(U, (m, keep)), "mj", Xt, "lj", "ml")                 # left vectors
         Q = _view(Vh, cd + (keep,))
+        ph.mark("rotate")
         Z = F.apply(rows, cols, Q)                                               # A Vh (next Z)
+        ph.mark("apply")
         res = _residual_norms(_view(Z, (m, keep)), Ul, sig, m, ke, eyes[ke])
+        ph.mark("residual")
+        if ph.out:
+            st["phase_s"] = dict(ph.out)
         smax = float(sig.to_numpy()[0])
         rel = float(res.max()) / smax if smax > 0.0 else 0.0
         if not math.isfinite(rel):
@@ -409,8 +419,9 @@ def _r_factors(Z: _ChunkedPair, dist, group):
 
 
 def _gram_sqrt(G: DeviceTensor, n: int) -> DeviceTensor:
-    """R' = Lambda_+^{1/2} W^T from the eigendecomposition G = W Lambda W^T of a Gram matrix
-    (negative rounding-noise eigenvalues clipped): R'^T R' = G to eps ||G||."""
+    """R' = Lambda_+^{1/2} W^T [r; pair] from the eigendecomposition G = W Lambda W^T of a Gram
+    matrix (negative rounding-noise eigenvalues clipped): R'^T R' = G to eps ||G||.
+    (`rfactor="gram_eigh"`: a full n x n eigendecomposition, kept for comparison.)"""
     from .tensor import eigh_trunc
 
     lam, W, _ = eigh_trunc(_view(G, (n, n)), n)          # sorted by |lambda|, W: n x n
@@ -419,8 +430,24 @@ def _gram_sqrt(G: DeviceTensor, n: int) -> DeviceTensor:
     return _scale_leg(R, 0, DeviceTensor.from_numpy(root, 1, G.ctx))
 
 
-def _r_factors_gram(F: TwoFactor):
-    """(R_ef, R_cd) as in `_r_factors`, from the Gram matrices of the two matricizations, which
+def _gram_chol(G: DeviceTensor, n: int, min_rank: int) -> DeviceTensor:
+    """L [pair; r] with L L^T = G to eps ||G||: diagonally pivoted Cholesky of the Gram matrix
+    on the device (`tnr_psd_factor`, csrc/pchol.cu), stopped at the numerical rank r.  L^T is an
+    R factor of the matricization up to a left orthogonal gauge -- all that atrg3d.jl:58-66
+    use of it.  Columns beyond the rank are zero; at least `min_rank` columns are returned so
+    that the truncated bond keeps the dimension the reference gives it."""
+    import ctypes as C
+
+    L = DeviceTensor.empty((n, n), 1, G.ctx)
+    r = C.c_int64(0)
+    G.ctx.call("tnr_psd_factor", G.ptr, n, L.ptr, C.byref(r))
+    r = min(n, max(int(r.value), int(min_rank), 1))
+    return DeviceTensor(L.buf[: n * r], (n, r), None, G.ctx)
+
+
+def _r_factors_gram(F: TwoFactor, chi: int, eigh: bool = False):
+    """(R_ef, R_cd) as in `_r_factors` (`eigh`: [r, pair]; default: the transposed Cholesky
+    form [pair, r]), from the Gram matrices of the two matricizations, which
     follow from the factors without ever forming Z = sum_i P Q:
         G[(e f),(e' f')] = sum_{i i'} PP[.. i .. i'] QQ[.. i .. i']   (O(chi^6) flop),
     each P/Q self-contraction running over that factor's open legs that are ROWS.  R' is the
@@ -440,19 +467,25 @@ def _r_factors_gram(F: TwoFactor):
         QQ = contract(F.Q, F.lq, F.Q, ren(F.lq), keep_q + ren(keep_q))
         G = contract(PP, keep_p + ren(keep_p), QQ, keep_q + ren(keep_q), pair + up)
         n = d[pair[0]] * d[pair[1]]
-        R = _gram_sqrt(G, n)
-        out.append(_view(R, (n, d[pair[0]], d[pair[1]])))
+        if eigh:
+            R = _gram_sqrt(G, n)
+            out.append(_view(R, (n, d[pair[0]], d[pair[1]])))
+        else:
+            L = _gram_chol(G, n, min(chi, n))
+            out.append(_view(L, (d[pair[0]], d[pair[1]], L.dims[1])))
     return out[0], out[1]
 
 
-def _projectors(Rl: DeviceTensor, Rrt: DeviceTensor, chi: int):
-    """atrg3d.jl:58-66 with Rl = R1 [r; p q] and Rrt = R2^T [r'; p q]:
+def _projectors(Rl: DeviceTensor, Rrt: DeviceTensor, chi: int, bond_last: bool = False):
+    """atrg3d.jl:58-66 with Rl = R1 [r; p q] and Rrt = R2^T [r'; p q] (`bond_last`: [p q; r] and
+    [p q; r'], the layout of the Cholesky factors):
     temp = Rl Rr,  U S V = svd_trunc(temp),  Pa[p q; k] = Rr V' S^-1/2,  Pb[k; p q] = S^-1/2 U' Rl."""
-    t = contract(Rl, "rpq", Rrt, "spq", "rs")
+    ll, lr = ("pqr", "pqs") if bond_last else ("rpq", "spq")
+    t = contract(Rl, ll, Rrt, lr, "rs")
     U, S, Vt, _ = svd_trunc(t, 1, chi)
     inv = _vec_map(S, 2, -0.5)
-    Pa = _scale_leg(contract(Rrt, "spq", Vt, "ks", "pqk"), 2, inv)
-    Pb = _scale_leg(contract(U, "rk", Rl, "rpq", "kpq"), 0, inv)
+    Pa = _scale_leg(contract(Rrt, lr, Vt, "ks", "pqk"), 2, inv)
+    Pb = _scale_leg(contract(U, "rk", Rl, ll, "kpq"), 0, inv)
     return Pa, Pb
 
 
@@ -523,18 +556,20 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     YDc = _ChunkedPair(YD, "b", width_b, rank, world)
     stats["chunks"] = {"AX": [len(p) for p in AXc.plans], "YD": [len(p) for p in YDc.plans],
                        "width": (width_a, width_b), "world": world}
-    if rfactor == "gram":
-        R1, R3 = _r_factors_gram(YD)
-        R2t, R4t = _r_factors_gram(AX)
+    if rfactor in ("gram", "gram_eigh"):
+        R1, R3 = _r_factors_gram(YD, chi, eigh=rfactor == "gram_eigh")
+        R2t, R4t = _r_factors_gram(AX, chi, eigh=rfactor == "gram_eigh")
     elif rfactor == "tsqr":
         R1, R3 = _r_factors(YDc, dist, group)      # left_orth(YD ...)   [r; 5 6], [r; 3 4]
         R2t, R4t = _r_factors(AXc, dist, group)    # right_orth(AX ...)^T
     else:
-        raise ValueError(f"rfactor must be 'tsqr' or 'gram', not {rfactor!r}")
+        raise ValueError(f"rfactor must be 'tsqr', 'gram' or 'gram_eigh', not {rfactor!r}")
     stats["rfactor"] = rfactor
+    if rfactor == "gram":
+        stats["gram_ranks"] = [R1.dims[-1], R2t.dims[-1], R3.dims[-1], R4t.dims[-1]]
     ph.mark("r_factors")
-    P1, P2 = _projectors(R1, R2t, chi)         # Proj_1 [5 6; k], Proj_2 [k; 5 6]
-    P3, P4 = _projectors(R3, R4t, chi)         # Proj_3 [3 4; k], Proj_4 [k; 3 4]
+    P1, P2 = _projectors(R1, R2t, chi, rfactor == "gram")     # Proj_1 [5 6; k], Proj_2 [k; 5 6]
+    P3, P4 = _projectors(R3, R4t, chi, rfactor == "gram")     # Proj_3 [3 4; k], Proj_4 [k; 3 4]
     del R1, R2t, R3, R4t
     ph.mark("projectors")
     # H[-1 -2;-3 -4] := YD[-1 -2;1 2 3 4] Proj_3[1 2;-3] Proj_1[3 4;-4]           :68

@@ -363,6 +363,15 @@ int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims,
     });
 }
 
+int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int64_t* rank_out) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(G && L && n >= 1, "psd_factor: bad arguments");
+        const long long r = psd_factor(&ctx->c, G, n, L);
+        if (rank_out) *rank_out = r;
+    });
+}
+
 int tnr_eigh_trunc(tnr_context* ctx, const double* MM, int64_t n, int chi, double* W, double* V,
                    int64_t* k_out, double* eps_out) {
     if (!ctx) return 1;
@@ -720,6 +729,7 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "subspace_svd") *value = (double)c.subspace_svd;
         else if (n == "persistent_jacobi") *value = (double)c.persistent_jacobi;
         else if (n == "qr_factorizations") *value = (double)c.qr_factorizations;
+        else if (n == "psd_factorizations") *value = (double)c.psd_factorizations;
         else if (n == "jacobi_limit_accepted") *value = (double)c.jacobi_limit_accepted;
         else if (n == "jacobi_not_converged") *value = (double)c.jacobi_not_converged;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;

@@ -7,7 +7,7 @@ mkdir -p "$OUT" "$HERE/.obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 pids=()
-for f in gemm_dmma gemm_tma gemm_ozaki permute elementwise jacobi qr tensor_ops schemes api; do
+for f in gemm_dmma gemm_tma gemm_ozaki permute elementwise jacobi qr pchol tensor_ops schemes api; do
   if [ ! -f "$HERE/.obj/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/.obj/$f.o" ] || \
      [ "$HERE/common.cuh" -nt "$HERE/.obj/$f.o" ] || [ "$HERE/tensor.hpp" -nt "$HERE/.obj/$f.o" ] || \
      [ "$HERE/schemes.hpp" -nt "$HERE/.obj/$f.o" ] || [ "$HERE/crt_math.cuh" -nt "$HERE/.obj/$f.o" ] || \

@@ -45,6 +45,7 @@ struct Counters {
     unsigned long long subspace_svd = 0;        // svd_trunc calls served by the subspace solver
     unsigned long long persistent_jacobi = 0;    // Jacobi iterations run as one cooperative launch
     unsigned long long qr_factorizations = 0;    // blocked Householder QR factorizations (qr.cu)
+    unsigned long long psd_factorizations = 0;   // pivoted Cholesky factorizations (pchol.cu)
     unsigned long long jacobi_limit_accepted = 0; // sweep limit reached with only rounding-level rotations left
     unsigned long long jacobi_not_converged = 0; // one-sided Jacobi runs that hit the sweep limit (an error is raised)
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi

@@ -76,6 +76,10 @@ void qr_q_times(Context* ctx, const QRWork& w, const double* X, long long ldx, l
 
 void qr_thin(Context* ctx, const double* A, long long m, long long n, double* Q, double* R);
 
+// ---- pchol.cu: G ~= L L^T for a symmetric PSD matrix (diagonally pivoted Cholesky without row
+// exchanges, blocked; columns >= the returned numerical rank are zero).  block <= 0: default.
+long long psd_factor(Context* ctx, const double* G, long long n, double* L, int block = 0);
+
 DT clone(const DT& a);
 DT permute(const DT& a, const std::vector<int>& perm);
 // out labels = lc; contracted labels = those in both la and lb and not in lc

@@ -24,7 +24,7 @@ ap.add_argument("--chi", type=int, default=48)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dense", action="store_true", help="the dense tnr_atrg3d_step instead")
 ap.add_argument("--block", type=int, default=None)
-ap.add_argument("--rfactor", choices=("tsqr", "gram"), default="tsqr",
+ap.add_argument("--rfactor", choices=("tsqr", "gram", "gram_eigh"), default="tsqr",
                 help="R factors by chunked TSQR (2 chi^8 flop each) or from the Gram matrices of the "
                      "factors (chi^6)")
 ap.add_argument("--phases", action="store_true",
