@@ -173,6 +173,14 @@ int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims,
  * factored ATRG_3D step obtains its four R factors this way from the chi^2 x chi^2 Gram matrices of
  * the matricizations of YD / AX (one launch per column + one DMMA GEMM per 64 columns). */
 int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int64_t* rank_out);
+/* In place: A (m x n, column major, m >= n) <- Q with orthonormal columns and the same column
+ * space (Q = A R^-1, R the Cholesky factor of A^T A; CholeskyQR2: Gram matrix and A R^-1 on the FP64
+ * tensor cores, twice).  The basis refresh BETWEEN the Rayleigh-Ritz steps of the block subspace
+ * iteration that serves `svd_trunc(...; trunc = truncrank(chi))` on operators too large to
+ * decompose (src/schemes/atrg3d.jl:35,43 at chi = 48); the Rayleigh-Ritz steps themselves, which
+ * decide the result, use tnr_svd_trunc.  *refused_out = 1 and A untouched when A^T A is not
+ * safely positive definite (rank deficient, cond(A) >~ 1e5): take tnr_qr / tnr_svd_trunc then. */
+int tnr_orthonormalize(tnr_context* ctx, double* A, int64_t m, int64_t n, int* refused_out);
 /* eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) (src/schemes/hotrg.jl:106,114,
  * hotrg3d.jl:94-98).  Keeps the chi eigenvalues of largest magnitude.  MM is n x n and is
  * not modified.  W: k signed eigenvalues, V: n x k. */

@@ -191,6 +191,24 @@ class EmulatedContext:
         assert m >= n, "orth_r: expects a tall matrix"
         _f(R, (n, n))[...] = np.linalg.qr(_f(T, (m, n)), mode="r")
 
+    def _tnr_orthonormalize(self, A, m, n, refused_out):
+        """csrc/pchol.cu: cholqr2 -- Q = A R^-1 with the Cholesky factor R (positive diagonal) of
+        A^T A, refused when the factor's diagonal spans more than 1e5 (or is not positive)."""
+        M = _f(A, (int(m), int(n)))
+        out = C.cast(refused_out, C.POINTER(C.c_int))
+        try:
+            R = np.linalg.cholesky(M.T @ M).T
+        except np.linalg.LinAlgError:
+            out[0] = 1
+            return
+        dg = np.diag(R)
+        if not np.all(np.isfinite(dg)) or not dg.min() > 1e-5 * dg.max():
+            out[0] = 1
+            return
+        q, r = np.linalg.qr(M)
+        M[...] = q * np.where(np.diag(r) < 0, -1.0, 1.0)
+        out[0] = 0
+
     PSD_REL = 8 * np.finfo(float).eps      # csrc/pchol.cu: PCHOL_REL
 
     def _tnr_psd_factor(self, G, n, L, rank_out):

@@ -83,3 +83,47 @@ def test_psd_factor_is_an_r_factor_for_the_projectors(tk, ctx):
     R2 = np.linalg.qr(B.T, mode="r").T
     ref = np.linalg.svd(R1 @ R2, compute_uv=False)
     assert np.abs(s[:12] - ref[:12]).max() <= 1e-12 * ref[0]
+
+
+def _orth(tk, ctx, A):
+    m, n = A.shape
+    Ad = tk.DeviceTensor.from_numpy(A)
+    refused = C.c_int(-1)
+    ctx.call("tnr_orthonormalize", Ad.ptr, m, n, C.byref(refused))
+    return Ad.to_numpy(), refused.value
+
+
+@pytest.mark.parametrize("m,n,cond", [(64, 1, 1.0), (300, 7, 10.0), (5000, 112, 1e3), (4096, 152, 1e2),
+                                      (4096, 153, 1e2), (20000, 256, 1e3), (110592, 112, 1e4)])
+def test_orthonormalize_cholqr2(tk, ctx, m, n, cond):
+    """tnr_orthonormalize: Q^T Q = I to rounding, Q = A R^-1 with R upper triangular, positive
+    diagonal (the thin QR factor with that sign convention)."""
+    rng = np.random.default_rng(m + n)
+    u, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (u * np.logspace(0, -np.log10(cond), n)) @ v.T
+    Q, refused = _orth(tk, ctx, A)
+    assert refused == 0
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 5e-14
+    R = Q.T @ A
+    assert np.abs(np.tril(R, -1)).max() <= 1e-12 * np.abs(R).max() and np.all(np.diag(R) > 0)
+    assert np.abs(Q @ R - A).max() <= 1e-12 * np.abs(A).max()
+    before = ctx.counters()["launches"]
+    _orth(tk, ctx, A)
+    assert ctx.counters()["launches"] - before <= 16          # GEMMs, split-K reductions, 2 one-CTA kernels
+
+
+def test_orthonormalize_refuses_ill_conditioned_and_leaves_input(tk, ctx):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((2000, 40))
+    A[:, 7] = A[:, 3] + 1e-9 * A[:, 5]                            # cond ~ 1e9
+    Q, refused = _orth(tk, ctx, A)
+    assert refused == 1 and np.array_equal(Q, A)
+    A[:, 7] = A[:, 3]                                             # exactly rank deficient
+    Q, refused = _orth(tk, ctx, A)
+    assert refused == 1 and np.array_equal(Q, A)
+    Z = np.zeros((100, 5))
+    Q, refused = _orth(tk, ctx, Z)
+    assert refused == 1
+    with pytest.raises(tk.TNRCudaError):
+        _orth(tk, ctx, rng.standard_normal((5, 9)))               # wide

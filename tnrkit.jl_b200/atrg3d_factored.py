@@ -197,9 +197,36 @@ def _residual_norms(Z: DeviceTensor, Ul: DeviceTensor, sig: DeviceTensor, m: int
     return np.sqrt(np.maximum(np.diag(g), 0.0))
 
 
+def _orthonormalize(M: DeviceTensor) -> bool:
+    """M (rows x cols, tall) <- orthonormal basis of its columns, in place (`tnr_orthonormalize`:
+    CholeskyQR2).  False: refused (ill-conditioned or rank deficient), M untouched."""
+    import ctypes as C
+
+    rows, cols = M.dims
+    if rows < cols:
+        return False
+    refused = C.c_int(1)
+    M.ctx.call("tnr_orthonormalize", M.ptr, rows, cols, C.byref(refused))
+    return refused.value == 0
+
+
+def _next_check(history, it: int, rel: float, tol: float, max_jump: int = 8) -> int:
+    """Iteration of the next Rayleigh-Ritz check: where the geometric rate seen between the last
+    two checks reaches tol / 2, at most `max_jump` iterations ahead; two iterations ahead
+    while no rate is known or the residual did not shrink."""
+    if history:
+        it0, rel0 = history[-1]
+        if 0.0 < rel < rel0 and it > it0:
+            rate = (rel / rel0) ** (1.0 / (it - it0))
+            need = math.log(0.5 * tol / rel) / math.log(rate)
+            return it + int(min(max_jump, max(1, math.ceil(need))))
+    return it + 2
+
+
 def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float = 1e-13,
                       maxit: int = 400, seed: int = 0x5EED, stats: dict | None = None,
-                      block: int | None = None, dense_fallback_elems: int = 1 << 27):
+                      block: int | None = None, dense_fallback_elems: int = 1 << 27,
+                      cholqr: bool = True):
     """svd_trunc(permute(T, (rows), (cols)); trunc = truncrank(chi)) for a TwoFactor T, without
     forming T.  Returns U [rows..., k], S [k], V [cols..., k]  (V is the TRANSPOSE of TensorKit's
     third factor: callers address legs by label, so no data is moved to transpose it).
@@ -237,19 +264,38 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     best, stalled = math.inf, 0
     Ul = sig = None
     eyes = {}
-    for it in range(1, maxit + 1):
-        U, S, _, _ = svd_trunc(_view(Z, (m, Z.dims[-1])), 1, NO_TRUNCATION)       # Z = U S W^T
-        s = S.to_numpy()
-        ph.mark("svd_Z")
-        keep = int(np.count_nonzero(s > 1e-14 * s[0]))
-        if keep == 0:
-            return dense_svd("zero operator")
+    # Rayleigh-Ritz (thin SVD of A^T U, residuals) only at the iterations `check`; in between
+    # the bases are just re-orthonormalised (CholeskyQR2 on the tensor cores).  The first checks
+    # give the convergence rate, later ones are placed where the tolerance is predicted.
+    check, history, checks, cheap_its = min(2, maxit), [], 0, 0
+    it = 0
+    while True:
+        it += 1
+        bz = Z.dims[-1]
+        Zm = _view(Z, (m, bz))
+        if cholqr and _orthonormalize(Zm):                 # U = orth(Z) in place
+            U, keep = Z, bz
+            ph.mark("orth")
+        else:
+            U, S, _, _ = svd_trunc(Zm, 1, NO_TRUNCATION)                          # Z = U S W^T
+            s = S.to_numpy()
+            ph.mark("svd_Z")
+            keep = int(np.count_nonzero(s > 1e-14 * s[0]))
+            if keep == 0:
+                return dense_svd("zero operator")
+            U = DeviceTensor(U.buf[: m * keep], rd + (keep,), None, ctx)
         ke = min(k, keep)     # rank(A) < chi: the block spans the whole range, the rest is zero
-        if ke not in eyes:
-            eyes[ke] = DeviceTensor.from_numpy(np.eye(ke), None, ctx)
-        U = DeviceTensor(U.buf[: m * keep], rd + (keep,), None, ctx)
         Y = F.apply(cols, rows, U)                                               # A^T U
         ph.mark("apply")
+        if cholqr and it < check and _orthonormalize(_view(Y, (n, keep))):       # Q = orth(A^T U)
+            ph.mark("orth")
+            Z = F.apply(rows, cols, Y)
+            ph.mark("apply")
+            cheap_its += 1
+            continue
+        checks += 1
+        if ke not in eyes:
+            eyes[ke] = DeviceTensor.from_numpy(np.eye(ke), None, ctx)
         Vh, sig, Xt, _ = svd_trunc(_view(Y, (n, keep)), 1, NO_TRUNCATION)        # Y = Vh sig Xt
         ph.mark("svd_Y")
         Ul = contract(_view(U, (m, keep)), "mj", Xt, "lj", "ml")                 # left vectors
@@ -273,7 +319,7 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
         best = min(best, rel)
         if stalled >= 3 and best <= 20 * tol:
             break
-        if stalled >= 12 or it == maxit:
+        if stalled >= 12 or it >= maxit:
             if m * n <= dense_fallback_elems:
                 log.warning("svd_topk_factored: residual %.2e after %d iterations (block %d); "
                             "dense SVD of the %d x %d matrix instead", best, it, b, m, n)
@@ -281,6 +327,9 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
                 return dense_svd("subspace iteration did not certify")
             raise _lib.TNRCudaError(f"svd_topk_factored: no convergence (residual {best:.2e} "
                                     f"after {it} iterations, block {b})")
+        check = min(maxit, _next_check(history, it, rel, tol))
+        history.append((it, rel))
+    st.update(checks=checks, cheap_iterations=cheap_its)
     st.update(iterations=it, dense=False, block=b, residual=rel, rank=ke)
     if ke == k:
         Uk = DeviceTensor(Ul.buf[: m * k].clone(), rd + (k,), None, ctx)

@@ -372,6 +372,14 @@ int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int6
     });
 }
 
+int tnr_orthonormalize(tnr_context* ctx, double* A, int64_t m, int64_t n, int* refused_out) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(A && refused_out && m >= n && n >= 1, "orthonormalize: bad arguments");
+        *refused_out = cholqr2(&ctx->c, A, m, n) ? 0 : 1;
+    });
+}
+
 int tnr_eigh_trunc(tnr_context* ctx, const double* MM, int64_t n, int chi, double* W, double* V,
                    int64_t* k_out, double* eps_out) {
     if (!ctx) return 1;
@@ -730,6 +738,8 @@ extern "C" int tnr_get_counter(tnr_context* ctx, const char* name, double* value
         else if (n == "persistent_jacobi") *value = (double)c.persistent_jacobi;
         else if (n == "qr_factorizations") *value = (double)c.qr_factorizations;
         else if (n == "psd_factorizations") *value = (double)c.psd_factorizations;
+        else if (n == "cholqr2") *value = (double)c.cholqr2;
+        else if (n == "cholqr2_refused") *value = (double)c.cholqr2_refused;
         else if (n == "jacobi_limit_accepted") *value = (double)c.jacobi_limit_accepted;
         else if (n == "jacobi_not_converged") *value = (double)c.jacobi_not_converged;
         else if (n == "subspace_fallbacks") *value = (double)c.subspace_fallbacks;

@@ -46,6 +46,8 @@ struct Counters {
     unsigned long long persistent_jacobi = 0;    // Jacobi iterations run as one cooperative launch
     unsigned long long qr_factorizations = 0;    // blocked Householder QR factorizations (qr.cu)
     unsigned long long psd_factorizations = 0;   // pivoted Cholesky factorizations (pchol.cu)
+    unsigned long long cholqr2 = 0;              // CholeskyQR2 orthonormalisations (pchol.cu)
+    unsigned long long cholqr2_refused = 0;      // ... refused (ill-conditioned): Householder path taken
     unsigned long long jacobi_limit_accepted = 0; // sweep limit reached with only rounding-level rotations left
     unsigned long long jacobi_not_converged = 0; // one-sided Jacobi runs that hit the sweep limit (an error is raised)
     unsigned long long subspace_fallbacks = 0;  // ... that fell back to full Jacobi

@@ -179,4 +179,128 @@ long long psd_factor(Context* ctx, const double* G, long long n, double* L, int 
     return rank;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CholeskyQR2: orthonormal basis of the columns of a tall, well-conditioned matrix with three
+// kinds of kernels only -- Gram matrix (DMMA GEMM), a one-CTA Cholesky + triangular inverse of the
+// small n x n matrix, and A R^-1 (DMMA GEMM) -- done twice, which brings ||Q^T Q - I|| from
+// cond(A)^2 eps to eps.  It is what the block subspace iterations (the truncated SVDs of
+// atrg3d.jl:35,43 on an implicit operator, and svd_topk / eigh_topk in tensor_ops.cu) run
+// BETWEEN their Rayleigh-Ritz steps: those steps decide the result and keep the Householder QR +
+// Jacobi path, the steps in between only have to keep the basis well conditioned.  Refuses
+// (A untouched) when the Cholesky factor shows cond(A) >~ 1e5 or is not positive definite; the
+// caller then takes the Householder path.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int CI_THREADS = 1024;
+constexpr int CI_SMEM_N = 152;     // n <= 152: the matrix lives in shared memory (<= 185 KB)
+
+// One CTA.  G (n x n, ld n, symmetric positive definite; upper triangle used) -> R in the upper
+// triangle of G (G = R^T R), X = R^-1 (upper triangular, strict lower part zero).
+// status[0] = 1 when a pivot is not positive / finite or min_k R_kk <= min_ratio * max_k R_kk.
+__global__ void __launch_bounds__(CI_THREADS) chol_inv_kernel(double* __restrict__ G, int n,
+                                                              double* __restrict__ X,
+                                                              double min_ratio, int use_smem,
+                                                              int* __restrict__ status) {
+    extern __shared__ double ci_sm[];
+    __shared__ double s_piv;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    double* M = use_smem ? ci_sm : G;
+    if (use_smem)
+        for (int e = tid; e < n * n; e += CI_THREADS) M[e] = G[e];
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    double rmin = 1e300, rmax = 0.0;           // thread 0 only
+    for (int k = 0; k < n; ++k) {
+        if (tid == 0) {
+            const double d = M[k + (long long)k * n];
+            if (!(d > 0.0) || !isfinite(d)) s_bad = 1;
+            const double r = sqrt(d > 0.0 ? d : 1.0);
+            s_piv = r;
+            rmin = fmin(rmin, r);
+            rmax = fmax(rmax, r);
+        }
+        __syncthreads();
+        if (s_bad) break;
+        const double piv = s_piv;
+        for (int j = k + tid; j < n; j += CI_THREADS)
+            M[k + (long long)j * n] = (j == k) ? piv : M[k + (long long)j * n] / piv;
+        __syncthreads();
+        const int w = n - k - 1;
+        for (int e = tid; e < w * w; e += CI_THREADS) {
+            const int i = k + 1 + e % w, j = k + 1 + e / w;
+            if (i <= j) M[i + (long long)j * n] -= M[k + (long long)i * n] * M[k + (long long)j * n];
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && (s_bad || !(rmin > min_ratio * rmax))) {
+        s_bad = 1;
+        status[0] = 1;
+    }
+    __syncthreads();
+    if (s_bad) return;
+    // X = R^-1 by back substitution, one thread per column
+    for (int j = tid; j < n; j += CI_THREADS) {
+        double* x = X + (long long)j * n;
+        for (int i = n - 1; i > j; --i) x[i] = 0.0;
+        x[j] = 1.0 / M[j + (long long)j * n];
+        for (int i = j - 1; i >= 0; --i) {
+            double sacc = 0.0;
+            for (int k = i + 1; k <= j; ++k) sacc = fma(M[i + (long long)k * n], x[k], sacc);
+            x[i] = -sacc / M[i + (long long)i * n];
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int e = tid; e < n * n; e += CI_THREADS) G[e] = M[e];
+    }
+}
+
+void chol_inv(Context* ctx, double* G, long long n, double* X, double min_ratio, int* status) {
+    const int use_smem = n <= CI_SMEM_N ? 1 : 0;
+    const size_t smem = use_smem ? (size_t)n * n * sizeof(double) : 0;
+    static bool configured = false;
+    if (!configured) {
+        TNR_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      CI_SMEM_N * CI_SMEM_N * (int)sizeof(double)));
+        configured = true;
+    }
+    chol_inv_kernel<<<1, CI_THREADS, smem, ctx->stream>>>(G, (int)n, X, min_ratio, use_smem, status);
+    TNR_CUDA(cudaGetLastError());
+    ctx->ctr.launches++;
+}
+
+}  // namespace
+
+// A (m x n, ld m, m >= n) <- Q with orthonormal columns spanning the columns of A, Q = A R^-1 for
+// the Cholesky factor R (positive diagonal) of A^T A.  Returns false and leaves A untouched when
+// the factor is not safely positive definite (rank deficient or cond(A) >~ 1e5).
+bool cholqr2(Context* ctx, double* A, long long m, long long n) {
+    TNR_CHECK(m >= n && n >= 1, "cholqr2: expects a tall matrix");
+    if (n > 1024 || m > 2147483647LL) return false;
+    double* G = dalloc(ctx, (size_t)2 * n * n);
+    double* X = G + n * n;
+    double* tmp = dalloc(ctx, (size_t)m * n);
+    int* d_status = nullptr;
+    TNR_CUDA(cudaMallocAsync((void**)&d_status, 2 * sizeof(int), ctx->stream));
+    TNR_CUDA(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), ctx->stream));
+    const int mi = (int)m, ni = (int)n;
+    gemm(ctx, 'T', 'N', ni, ni, mi, 1.0, A, m, A, m, 0.0, G, n);
+    chol_inv(ctx, G, n, X, 1e-5, d_status);
+    gemm(ctx, 'N', 'N', mi, ni, ni, 1.0, A, m, X, n, 0.0, tmp, m);
+    gemm(ctx, 'T', 'N', ni, ni, mi, 1.0, tmp, m, tmp, m, 0.0, G, n);
+    chol_inv(ctx, G, n, X, 0.5, d_status + 1);        // second pass: R ~ I
+    int st[2] = {1, 1};
+    TNR_CUDA(cudaMemcpyAsync(st, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TNR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const bool ok = st[0] == 0 && st[1] == 0;
+    if (ok) gemm(ctx, 'N', 'N', mi, ni, ni, 1.0, tmp, m, X, n, 0.0, A, m);
+    TNR_CUDA(cudaFreeAsync(d_status, ctx->stream));
+    dfree(ctx, tmp);
+    dfree(ctx, G);
+    if (ok) ctx->ctr.cholqr2++; else ctx->ctr.cholqr2_refused++;
+    return ok;
+}
+
 }  // namespace tnr

@@ -80,6 +80,10 @@ void qr_thin(Context* ctx, const double* A, long long m, long long n, double* Q,
 // exchanges, blocked; columns >= the returned numerical rank are zero).  block <= 0: default.
 long long psd_factor(Context* ctx, const double* G, long long n, double* L, int block = 0);
 
+// A (m x n, ld m) <- orthonormal basis of its columns by CholeskyQR2 (Gram GEMM, one-CTA Cholesky +
+// inverse, GEMM; twice).  false = refused (not safely positive definite), A untouched.
+bool cholqr2(Context* ctx, double* A, long long m, long long n);
+
 DT clone(const DT& a);
 DT permute(const DT& a, const std::vector<int>& perm);
 // out labels = lc; contracted labels = those in both la and lb and not in lc
