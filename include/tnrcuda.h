@@ -62,6 +62,9 @@ int tnr_get_counter(tnr_context* ctx, const char* name, double* value);
  * "permute_tpc" (1..8) and "permute_chunk_below" (bytes) tune the TMA-fed copy;
  * "hotrg3d_pk_budget_mb": megabytes of absorbed operands Pk_d the HOTRG_3D z-compression holds
  * at once (default 49152; the d loop is blocked into windows, also capped by the free memory).
+ * "disable_cholqr" = 1: the subspace solvers re-orthonormalise their bases by Householder QR
+ * instead of CholeskyQR2; "jacobi_max_bc" = 4 | 8 (default) | 16: largest column block of the
+ * shared-memory Jacobi kernels (A/B tests).
  * Unknown keys and out-of-range values are errors. */
 int tnr_set_option(tnr_context* ctx, const char* key, int64_t value);
 /* CUDA-event timing of the dominant kernel (DMMA GEMM launches above 1e11 flop) on the
@@ -173,6 +176,9 @@ int tnr_orth_r(tnr_context* ctx, const double* T, int rank, const int64_t* dims,
  * factored ATRG_3D step obtains its four R factors this way from the chi^2 x chi^2 Gram matrices of
  * the matricizations of YD / AX (one launch per column + one DMMA GEMM per 64 columns). */
 int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int64_t* rank_out);
+/* x[i] = uniform(-1, 1) from the splitmix64 hash of (seed, i): the start block of the subspace
+ * iterations, generated where it is used (deterministic, identical on every rank of a sharded run). */
+int tnr_fill_random(tnr_context* ctx, double* x, int64_t n, uint64_t seed);
 /* In place: A (m x n, column major, m >= n) <- Q with orthonormal columns and the same column
  * space (Q = A R^-1, R the Cholesky factor of A^T A; CholeskyQR2: Gram matrix and A R^-1 on the FP64
  * tensor cores, twice).  The basis refresh BETWEEN the Rayleigh-Ritz steps of the block subspace

@@ -191,6 +191,17 @@ class EmulatedContext:
         assert m >= n, "orth_r: expects a tall matrix"
         _f(R, (n, n))[...] = np.linalg.qr(_f(T, (m, n)), mode="r")
 
+    def _tnr_fill_random(self, x, n, seed):
+        """csrc/elementwise.cu: fill_random_kernel (splitmix64 of seed + golden * (i + 1))."""
+        n = int(n)
+        with np.errstate(over="ignore"):
+            z = np.uint64(int(seed) & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * \
+                np.arange(1, n + 1, dtype=np.uint64)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        _flat(x, n)[...] = (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
     def _tnr_orthonormalize(self, A, m, n, refused_out):
         """csrc/pchol.cu: cholqr2 -- Q = A R^-1 with the Cholesky factor R (positive diagonal) of
         A^T A, refused when the factor's diagonal spans more than 1e5 (or is not positive)."""

@@ -127,3 +127,14 @@ def test_orthonormalize_refuses_ill_conditioned_and_leaves_input(tk, ctx):
     assert refused == 1
     with pytest.raises(tk.TNRCudaError):
         _orth(tk, ctx, rng.standard_normal((5, 9)))               # wide
+
+
+def test_fill_random_matches_the_host_restatement(tk, ctx):
+    n = 100003
+    x = tk.DeviceTensor.empty((n,), 1, ctx)
+    ctx.call("tnr_fill_random", x.ptr, n, 0x5EED)
+    ref = np.zeros(n)
+    EmulatedContext()._tnr_fill_random(ref.ctypes.data, n, 0x5EED)
+    got = x.to_numpy()
+    assert np.array_equal(got, ref)
+    assert abs(got.mean()) < 0.01 and abs(got.std() - 1 / np.sqrt(3)) < 0.01 and np.abs(got).max() < 1.0

@@ -70,6 +70,7 @@ _SIGNATURES = {
                       _c_i64p, C.POINTER(C.c_double)],
     "tnr_orth_r": [C.c_void_p, _c_dp, C.c_int, _c_i64p, C.c_int, _c_dp],
     "tnr_psd_factor": [C.c_void_p, _c_dp, C.c_int64, _c_dp, _c_i64p],
+    "tnr_fill_random": [C.c_void_p, _c_dp, C.c_int64, C.c_uint64],
     "tnr_orthonormalize": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, C.POINTER(C.c_int)],
     "tnr_qr": [C.c_void_p, _c_dp, C.c_int64, C.c_int64, _c_dp, _c_dp],
     "tnr_eigh_trunc": [C.c_void_p, _c_dp, C.c_int64, C.c_int, _c_dp, _c_dp, _c_i64p,

@@ -223,10 +223,29 @@ def _next_check(history, it: int, rel: float, tol: float, max_jump: int = 8) -> 
     return it + 2
 
 
+def _apply_sharded(F: TwoFactor, rows: str, cols: str, V: DeviceTensor, shard) -> DeviceTensor:
+    """F.apply(rows, cols, V) with the block columns of V (its last leg) dealt to the ranks of a
+    sharded run and the products all-gathered along that leg: every rank ends with the same
+    bytes, so everything computed from them stays bit-identical between the replicas."""
+    if shard is None or shard[3] == 1 or V.dims[-1] < shard[3]:
+        return F.apply(rows, cols, V)
+    from .schemes import allgather_last_leg, shard_range
+
+    _, group, rank, world = shard
+    nb = V.dims[-1]
+    lo, hi = shard_range(nb, rank, world)
+    out = DeviceTensor.empty(tuple(F.dim(c) for c in rows) + (nb,), None, F.ctx)
+    if hi > lo:
+        part = F.apply(rows, cols, _slice_last(V, lo, hi))
+        _slice_last(out, lo, hi).buf.copy_(part.buf[: part.size])
+    allgather_last_leg(out.buf, out.dims, group)
+    return out
+
+
 def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float = 1e-13,
                       maxit: int = 400, seed: int = 0x5EED, stats: dict | None = None,
                       block: int | None = None, dense_fallback_elems: int = 1 << 27,
-                      cholqr: bool = True):
+                      cholqr: bool = True, shard=None):
     """svd_trunc(permute(T, (rows), (cols)); trunc = truncrank(chi)) for a TwoFactor T, without
     forming T.  Returns U [rows..., k], S [k], V [cols..., k]  (V is the TRANSPOSE of TensorKit's
     third factor: callers address legs by label, so no data is moved to transpose it).
@@ -256,10 +275,14 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     if b >= r:
         st.update(iterations=0)
         return dense_svd("block covers the matrix")
-    rng = np.random.default_rng(seed)
-    Q = DeviceTensor.from_numpy(rng.standard_normal(cd + (b,)), None, ctx)
+    Q = DeviceTensor.empty(cd + (b,), None, ctx)      # start block: generated on the device
+    ctx.call("tnr_fill_random", Q.ptr, Q.size, int(seed))
     ph = _Phases(ctx)
-    Z = F.apply(rows, cols, Q)
+
+    def op(r_, c_, V):      # operator products; block columns dealt to the ranks of a sharded run
+        return _apply_sharded(F, r_, c_, V, shard)
+
+    Z = op(rows, cols, Q)
     ph.mark("apply")
     best, stalled = math.inf, 0
     Ul = sig = None
@@ -285,11 +308,11 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
                 return dense_svd("zero operator")
             U = DeviceTensor(U.buf[: m * keep], rd + (keep,), None, ctx)
         ke = min(k, keep)     # rank(A) < chi: the block spans the whole range, the rest is zero
-        Y = F.apply(cols, rows, U)                                               # A^T U
+        Y = op(cols, rows, U)                                               # A^T U
         ph.mark("apply")
         if cholqr and it < check and _orthonormalize(_view(Y, (n, keep))):       # Q = orth(A^T U)
             ph.mark("orth")
-            Z = F.apply(rows, cols, Y)
+            Z = op(rows, cols, Y)
             ph.mark("apply")
             cheap_its += 1
             continue
@@ -301,7 +324,7 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
         Ul = contract(_view(U, (m, keep)), "mj", Xt, "lj", "ml")                 # left vectors
         Q = _view(Vh, cd + (keep,))
         ph.mark("rotate")
-        Z = F.apply(rows, cols, Q)                                               # A Vh (next Z)
+        Z = op(rows, cols, Q)                                               # A Vh (next Z)
         ph.mark("apply")
         res = _residual_norms(_view(Z, (m, keep)), Ul, sig, m, ke, eyes[ke])
         ph.mark("residual")
@@ -494,6 +517,48 @@ def _gram_chol(G: DeviceTensor, n: int, min_rank: int) -> DeviceTensor:
     return DeviceTensor(L.buf[: n * r], (n, r), None, G.ctx)
 
 
+def _gram_matrix(F: TwoFactor, pair: str) -> DeviceTensor:
+    """G[(p q),(p' q')] of the matricization of F = sum_i P Q with columns `pair`, from the factors."""
+    up = pair.upper()
+    ren = lambda lab: "".join({pair[0]: up[0], pair[1]: up[1], BOND: "I"}.get(c, c) for c in lab)  # noqa: E731
+    keep_p = "".join(c for c in F.lp if c in pair or c == BOND)
+    keep_q = "".join(c for c in F.lq if c in pair or c == BOND)
+    PP = contract(F.P, F.lp, F.P, ren(F.lp), keep_p + ren(keep_p))
+    QQ = contract(F.Q, F.lq, F.Q, ren(F.lq), keep_q + ren(keep_q))
+    return contract(PP, keep_p + ren(keep_p), QQ, keep_q + ren(keep_q), pair + up)
+
+
+def _projectors_gram_dealt(YD: TwoFactor, AX: TwoFactor, chi: int, shard, stats: dict):
+    """rfactor="gram" on a sharded run: the two projector pairs of atrg3d.jl:58-66 are independent
+    ((e f): Proj_1 / Proj_2, (c d): Proj_3 / Proj_4), so rank 0 builds one pair and rank 1 the
+    other -- Gram matrices, Cholesky factors, truncated SVD -- and the chi^2 x chi projectors are
+    broadcast; nothing of size chi^4 travels."""
+    dist, group, rank, world = shard
+    out, ranks = [], {}
+    for gi, pair in enumerate(("ef", "cd")):
+        owner = gi % world
+        d0, d1 = YD.dim(pair[0]), YD.dim(pair[1])
+        n = d0 * d1
+        kk = min(chi, n)
+        if rank == owner:
+            Ll = _gram_chol(_gram_matrix(YD, pair), n, kk)
+            Lr = _gram_chol(_gram_matrix(AX, pair), n, kk)
+            ranks[pair] = [Ll.dims[1], Lr.dims[1]]
+            Pa, Pb = _projectors(_view(Ll, (d0, d1, Ll.dims[1])), _view(Lr, (d0, d1, Lr.dims[1])),
+                                 chi, True)
+            assert Pa.dims == (d0, d1, kk) and Pb.dims == (kk, d0, d1), (Pa.dims, Pb.dims)
+        else:
+            Pa = DeviceTensor.empty((d0, d1, kk), None, YD.ctx)
+            Pb = DeviceTensor.empty((kk, d0, d1), None, YD.ctx)
+        src = dist.get_global_rank(group, owner) if group is not None else owner
+        dist.broadcast(Pa.buf, src=src, group=group)
+        dist.broadcast(Pb.buf, src=src, group=group)
+        out += [Pa, Pb]
+    stats["gram_ranks"] = ranks
+    stats["projector_owners"] = [0, 1 % world]
+    return out
+
+
 def _r_factors_gram(F: TwoFactor, chi: int, eigh: bool = False):
     """(R_ef, R_cd) as in `_r_factors` (`eigh`: [r, pair]; default: the transposed Cholesky
     form [pair, r]), from the Gram matrices of the two matricizations, which
@@ -508,13 +573,7 @@ def _r_factors_gram(F: TwoFactor, chi: int, eigh: bool = False):
     d = {c: F.dim(c) for c in LEGS}
     out = []
     for pair in ("ef", "cd"):
-        up = pair.upper()
-        ren = lambda lab: "".join({pair[0]: up[0], pair[1]: up[1], BOND: "I"}.get(c, c) for c in lab)  # noqa: E731
-        keep_p = "".join(c for c in F.lp if c in pair or c == BOND)
-        keep_q = "".join(c for c in F.lq if c in pair or c == BOND)
-        PP = contract(F.P, F.lp, F.P, ren(F.lp), keep_p + ren(keep_p))
-        QQ = contract(F.Q, F.lq, F.Q, ren(F.lq), keep_q + ren(keep_q))
-        G = contract(PP, keep_p + ren(keep_p), QQ, keep_q + ren(keep_q), pair + up)
+        G = _gram_matrix(F, pair)
         n = d[pair[0]] * d[pair[1]]
         if eigh:
             R = _gram_sqrt(G, n)
@@ -578,7 +637,8 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     F = T.relabel()
     # U, S, V = svd_trunc(permute(T, ((2,5,6),(3,4,1))))                         atrg3d.jl:35
     st = {}
-    fU, fS, fV = svd_topk_factored(F, "bef", "cda", chi, tol=tol, stats=st, block=block)   # [i2 i5 i6 k], [i3 i4 i1 k]
+    sh = (dist, group, rank, world) if world > 1 else None
+    fU, fS, fV = svd_topk_factored(F, "bef", "cda", chi, tol=tol, stats=st, block=block, shard=sh)   # [i2 i5 i6 k], [i3 i4 i1 k]
     stats["svd"].append(st)
     ph.mark("svd_T")
     US = _scale_leg(fU.clone(), 3, fS)        # C = U*S
@@ -587,7 +647,7 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     # legs are [kB i5 i6 | i3 i4 kC] = "bef|cda" with US = [i e f a], SV = [c d i b]   :41-43
     M = TwoFactor(US, "iefa", SV, "cdib", "befcda")
     st = {}
-    gU, gS, gV = svd_topk_factored(M, "bef", "cda", chi, tol=tol, stats=st, block=block)   # [m2 m5 m6 k], [m3 m4 m1 k]
+    gU, gS, gV = svd_topk_factored(M, "bef", "cda", chi, tol=tol, stats=st, block=block, shard=sh)   # [m2 m5 m6 k], [m3 m4 m1 k]
     stats["svd"].append(st)
     ph.mark("svd_M")
     del M, US, SV
@@ -605,7 +665,10 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     YDc = _ChunkedPair(YD, "b", width_b, rank, world)
     stats["chunks"] = {"AX": [len(p) for p in AXc.plans], "YD": [len(p) for p in YDc.plans],
                        "width": (width_a, width_b), "world": world}
-    if rfactor in ("gram", "gram_eigh"):
+    dealt = rfactor == "gram" and world > 1
+    if dealt:
+        P1, P2, P3, P4 = _projectors_gram_dealt(YD, AX, chi, (dist, group, rank, world), stats)
+    elif rfactor in ("gram", "gram_eigh"):
         R1, R3 = _r_factors_gram(YD, chi, eigh=rfactor == "gram_eigh")
         R2t, R4t = _r_factors_gram(AX, chi, eigh=rfactor == "gram_eigh")
     elif rfactor == "tsqr":
@@ -614,12 +677,13 @@ def atrg3d_substep_factored(T: TwoFactor, chi: int, max_chunk_elems: int = 1 << 
     else:
         raise ValueError(f"rfactor must be 'tsqr', 'gram' or 'gram_eigh', not {rfactor!r}")
     stats["rfactor"] = rfactor
-    if rfactor == "gram":
-        stats["gram_ranks"] = [R1.dims[-1], R2t.dims[-1], R3.dims[-1], R4t.dims[-1]]
-    ph.mark("r_factors")
-    P1, P2 = _projectors(R1, R2t, chi, rfactor == "gram")     # Proj_1 [5 6; k], Proj_2 [k; 5 6]
-    P3, P4 = _projectors(R3, R4t, chi, rfactor == "gram")     # Proj_3 [3 4; k], Proj_4 [k; 3 4]
-    del R1, R2t, R3, R4t
+    if not dealt:
+        if rfactor == "gram":
+            stats["gram_ranks"] = [R1.dims[-1], R2t.dims[-1], R3.dims[-1], R4t.dims[-1]]
+        ph.mark("r_factors")
+        P1, P2 = _projectors(R1, R2t, chi, rfactor == "gram")     # Proj_1 [5 6; k], Proj_2 [k; 5 6]
+        P3, P4 = _projectors(R3, R4t, chi, rfactor == "gram")     # Proj_3 [3 4; k], Proj_4 [k; 3 4]
+        del R1, R2t, R3, R4t
     ph.mark("projectors")
     # H[-1 -2;-3 -4] := YD[-1 -2;1 2 3 4] Proj_3[1 2;-3] Proj_1[3 4;-4]           :68
     H, lh = _squeeze(YDc, P3, "cdC", P1, "efD", dist, group)     # [a C D b]

@@ -172,6 +172,11 @@ int tnr_set_option(tnr_context* ctx, const char* key, int64_t value) {
         else if (std::strcmp(key, "disable_block_jacobi") == 0) ctx->c.disable_block_jacobi = value != 0;
         else if (std::strcmp(key, "disable_precondition") == 0) ctx->c.disable_precondition = value != 0;
         else if (std::strcmp(key, "disable_qr") == 0) ctx->c.disable_qr = value != 0;
+        else if (std::strcmp(key, "disable_cholqr") == 0) ctx->c.disable_cholqr = value != 0;
+        else if (std::strcmp(key, "jacobi_max_bc") == 0) {
+            TNR_CHECK(value == 4 || value == 8 || value == 16, "jacobi_max_bc: 4, 8 (default) or 16");
+            ctx->c.jacobi_max_bc = (int)value;
+        }
         else if (std::strcmp(key, "jacobi_max_sweeps") == 0) {
             TNR_CHECK(value >= 1 && value <= 1000, "jacobi_max_sweeps: 1..1000");
             ctx->c.jacobi_max_sweeps = (int)value;
@@ -369,6 +374,14 @@ int tnr_psd_factor(tnr_context* ctx, const double* G, int64_t n, double* L, int6
         TNR_CHECK(G && L && n >= 1, "psd_factor: bad arguments");
         const long long r = psd_factor(&ctx->c, G, n, L);
         if (rank_out) *rank_out = r;
+    });
+}
+
+int tnr_fill_random(tnr_context* ctx, double* x, int64_t n, uint64_t seed) {
+    if (!ctx) return 1;
+    return guard(ctx, [&] {
+        TNR_CHECK(x && n >= 0, "fill_random: bad arguments");
+        fill_random(&ctx->c, x, n, seed);
     });
 }
 

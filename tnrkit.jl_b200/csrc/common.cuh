@@ -77,6 +77,8 @@ struct Context {
     bool disable_precondition = false;  // no Gram preconditioning of tall Jacobi problems
     int jacobi_max_sweeps = 40;  // a Jacobi iteration that needs more raises an error
     bool disable_persistent_jacobi = false;  // one launch per Jacobi round + host sync per sweep (round 1)
+    bool disable_cholqr = false;  // subspace bases: Householder QR instead of CholeskyQR2 (A/B tests)
+    int jacobi_max_bc = 8;  // largest column block of the shared-memory Jacobi (16 | 8 | 4); 8: twice the CTAs of 16 and one pass of the 8 warps per inner round
     bool disable_qr = false;  // tall problems: Gram-preconditioned Jacobi (round 1) instead of Householder QR + Jacobi of R
     double timed_flops = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;

@@ -450,8 +450,13 @@ int jacobi_orthogonalize(Context* ctx, double* G, long long m, long long n, long
     // block variant when a pair of column blocks (G and V columns) fits in shared memory
     const long long rows = m + (V ? n : 0);
     int BC = 0;
+    // Time of a sweep ~ (n / BC rounds) x (2 BC - 1 inner rounds) x ceil(BC / 8 warps) pair
+    // rotations: BC = 16 runs two passes of the 8 warps per inner round on half as many CTAs as
+    // BC = 8 (n = 256: 15 x 62 against 31 x 15 rotation times per sweep, measured 13 ms per
+    // Ritz problem on 8 CTAs in profiles/r02_share_trg128_potts_qr.md), so 8 is the default cap.
     for (int cand : {16, 8, 4})
-        if (!BC && 2LL * cand * rows * 8 <= 200 * 1024 && n >= 2 * cand) BC = cand;
+        if (!BC && cand <= ctx->jacobi_max_bc && 2LL * cand * rows * 8 <= 200 * 1024 &&
+            n >= 2 * cand) BC = cand;
     if (BC && !ctx->disable_block_jacobi) {
         const int nblk = (int)((n + BC - 1) / BC);
         const int nblk_pad = (nblk + 1) & ~1;

@@ -296,6 +296,14 @@ void h2d(Context* ctx, double* dst, const double* src, size_t n) {
 // (columns of Y are expected to be roughly equilibrated; directions below 1e-14 relative
 // weight are dropped, i.e. set to zero).
 DT gram_orthonormalize(Context* ctx, const DT& Y, long long n, long long b) {
+    if (!ctx->disable_cholqr && !ctx->disable_qr && n >= 2 * b) {
+        // the bases handed in here are random (start) or Ritz-rotated images equilibrated by
+        // 1/|theta| (nearly orthogonal columns): cond ~ 1, where CholeskyQR2 -- four GEMMs and two
+        // one-CTA kernels -- is as orthonormal as Householder (b launches of the panel kernel +
+        // the formation of Q).  Refused (ill conditioned): Householder below.
+        DT Q = clone(DT::view(ctx, Y.p, {n, b}));
+        if (cholqr2(ctx, Q.p, n, b)) return Q;
+    }
     if (!ctx->disable_qr && n >= b) {
         // Householder QR: Q = H_1 ... H_b [I; 0] is orthonormal to rounding whatever the
         // conditioning of Y, and no b x b eigenproblem is solved
