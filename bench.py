@@ -502,7 +502,8 @@ def run_gpu(args):
                             f"beta_c) truncrank({chi}); timed steps are RG iterations "
                             f"{first_iter}..{first_iter + K - 1} of run! (legs {state_dims()})" +
                             (f"; {'factored' if scheme.factors is not None else 'dense'} step, "
-                             f"R factors: {args.rfactor}" if atrg else ""),
+                             f"R factors: {(_atrg_stats() or {}).get('rfactor', args.rfactor)}"
+                             if atrg else ""),
                 "time_budget_s": budget,
                 "time_box": (f"{K} of {args.steps} requested timed steps and {w_done} of "
                              f"{args.warmup} requested warm-up iterations fit the wall budget; "
@@ -510,8 +511,10 @@ def run_gpu(args):
                              "a steady-state step") if (K < args.steps or w_done < args.warmup)
                 else "all requested steps ran",
                 "parallelism": "1 GPU" if world == 1 else
-                (f"chunks of the open bond of AX / YD dealt to {world} GPUs; all-gathers of the "
-                 "chunk R factors and of H / G (NCCL)") if atrg else
+                (f"{world} GPUs: block columns of the subspace-iteration products and chunks of the "
+                 "open bond of AX / YD (H, G) dealt to the ranks and all-gathered (NCCL), the two "
+                 "projector pairs built on ranks 0 / 1 and broadcast; orthonormalisations and "
+                 "Rayleigh-Ritz steps replicated") if atrg else
                 f"open x-bond sharded over {world} GPUs; projector halves dealt to the ranks "
                 "and broadcast; exchange: " +
                 ("every T' slab stored to all ranks over NVLink by the kernel that produces it "
@@ -558,9 +561,10 @@ def run_gpu(args):
                 # run: see profiles/ (ncu --set full raw export of this kernel)
                 "traffic": None,
                 "kernel": ("all DMMA GEMM launches of the factored ATRG_3D step (chunk "
-                           "contractions, R factors, subspace iterations); when no launch reaches "
-                           "1e11 flop `achieved` is the GEMM flop of the step over the STEP time: "
-                           "the step is launch bound, not tensor bound") if atrg else
+                           "contractions, Gram matrices, subspace iterations); when no launch reaches "
+                           "1e11 flop `achieved` is the GEMM flop of the step over the STEP time "
+                           "(GEMMs + orthonormalisations + Rayleigh-Ritz steps + projector SVDs)")
+                if atrg else
                           ("gemm_dmma_tma_kernel (TMA + mbarrier producer warp, 8 DMMA consumer "
                            "warps; the (f,d)-chunked chi^3 x chi^3 x chi^3 contraction and the "
                            "projector Gram GEMMs above 1e11 flop)") if args.engine == "dmma" else
@@ -595,7 +599,9 @@ def main():
     ap.add_argument("--workload", default="hotrg3d", choices=["hotrg3d", "atrg3d"],
                     help="hotrg3d: the headline (BASELINE.json metric, configs[4], chi=24); atrg3d: "
                          "configs[3] (use --chi 48), same time box and JSON contract")
-    ap.add_argument("--rfactor", default="tsqr", choices=["tsqr", "gram", "gram_eigh"])
+    ap.add_argument("--rfactor", default=None, choices=["tsqr", "gram", "gram_eigh"],
+                    help="atrg3d: R factors of the factored step (default: the scheme's own choice, "
+                         "'gram' from chi = 40)")
     ap.add_argument("--factored", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--crt-moduli", type=int, default=16)

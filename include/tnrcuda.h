@@ -185,7 +185,8 @@ int tnr_fill_random(tnr_context* ctx, double* x, int64_t n, uint64_t seed);
  * iteration that serves `svd_trunc(...; trunc = truncrank(chi))` on operators too large to
  * decompose (src/schemes/atrg3d.jl:35,43 at chi = 48); the Rayleigh-Ritz steps themselves, which
  * decide the result, use tnr_svd_trunc.  *refused_out = 1 and A untouched when A^T A is not
- * safely positive definite (rank deficient, cond(A) >~ 1e5): take tnr_qr / tnr_svd_trunc then. */
+ * safely positive definite (rank deficient, cond(A) >~ 1e5) or n > 152: take tnr_qr /
+ * tnr_svd_trunc then. */
 int tnr_orthonormalize(tnr_context* ctx, double* A, int64_t m, int64_t n, int* refused_out);
 /* eigh_trunc!(project_hermitian!(MM); trunc = truncrank(chi)) (src/schemes/hotrg.jl:106,114,
  * hotrg3d.jl:94-98).  Keeps the chi eigenvalues of largest magnitude.  MM is n x n and is

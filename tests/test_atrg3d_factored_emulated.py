@@ -282,7 +282,9 @@ def _worker(rank, world, port, chi, n, budget, rfactor, q):
 
 @pytest.mark.parametrize("chi,budget,rfactor", [(4, 1 << 28, "tsqr"),    # even split
                                                 (5, 5 ** 5, "tsqr"),      # ragged 3 + 2, width 1
-                                                (6, 2000, "gram")])       # only H / G are sharded
+                                                (6, 2000, "gram"),        # dealt projector pairs
+                                                (10, 50000, "gram")])     # + sharded products of the
+#                                                 subspace iterations (block 74 of 1000 columns)
 def test_factored_atrg3d_sharded_world2(chi, budget, rfactor):
     import torch.multiprocessing as mp
 

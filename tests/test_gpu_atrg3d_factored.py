@@ -2,6 +2,7 @@
 (tnrkit.jl_b200/atrg3d_factored.py) through the real C ABI -- `tnr_orth_r`, the implicit products,
 the subspace-iteration SVD, chunked TSQR -- against the oracle, against the dense device step
 (`tnr_atrg3d_step`) and, on a box with 2 GPUs, sharded over NCCL."""
+import json
 import os
 import socket
 import sys
@@ -96,7 +97,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, chi, n, q):
+def _worker(rank, world, port, chi, n, rfactor, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -108,34 +109,43 @@ def _worker(rank, world, port, chi, n, q):
                             device_id=torch.device("cuda", rank))
     import tnrkit.jl_b200 as tk
 
-    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=True, max_chunk_elems=chi ** 5)
+    from tnrkit.jl_b200 import atrg3d_factored as af
+
+    s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), shard=True, max_chunk_elems=chi ** 5,
+                   rfactor=rfactor, block=None if chi < 6 else 2 * chi + 2)
     got = tk.run(s, tk.truncrank(chi), tk.maxiter(n), verbosity=0)
-    q.put((rank, got))
+    q.put((rank, (got, json.loads(json.dumps(af.LAST_STATS, default=str)))))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_factored_atrg3d_sharded_two_gpus():
+@pytest.mark.parametrize("chi,n,rfactor", [(5, 2, "tsqr"),     # ragged ownership of the open bond: 3 + 2
+                                           (10, 3, "gram")])   # sharded products of the subspace iteration (block 22 of 1000), dealt projector pairs
+def test_factored_atrg3d_sharded_two_gpus(chi, n, rfactor):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import tnrkit.jl_b200 as tk
+    from conditioning import checked_oracle_norms
 
-    chi, n = 5, 2      # ragged ownership of the open bond: 3 + 2
+    ref = np.array(checked_oracle_norms("ATRG_3D", chi, n))       # refuses ill-conditioned cases
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, chi, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, chi, n, rfactor, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    ref = np.array(o.run(o.ATRG_3D(tk.classical_ising_3D(tk.Trivial)), chi, n))
     for r in range(2):
-        got = np.array(res[r])
+        got = np.array(res[r][0])
         assert np.max(np.abs(got - ref) / np.abs(ref)) <= RTOL, r
-    assert np.max(np.abs(np.array(res[0]) - np.array(res[1]))) <= 1e-12 * np.max(np.abs(ref))
+        assert res[r][1]["rfactor"] == rfactor
+    assert res[0][0] == res[1][0]          # replicas stay bit-identical
+    if rfactor == "gram":
+        assert res[0][1]["projector_owners"] == [0, 1]
+        assert all(not st["dense"] and st["iterations"] >= 2 for st in res[0][1]["svd"])

@@ -94,7 +94,7 @@ def _orth(tk, ctx, A):
 
 
 @pytest.mark.parametrize("m,n,cond", [(64, 1, 1.0), (300, 7, 10.0), (5000, 112, 1e3), (4096, 152, 1e2),
-                                      (4096, 153, 1e2), (20000, 256, 1e3), (110592, 112, 1e4)])
+                                      (20000, 128, 1e3), (110592, 112, 1e4)])
 def test_orthonormalize_cholqr2(tk, ctx, m, n, cond):
     """tnr_orthonormalize: Q^T Q = I to rounding, Q = A R^-1 with R upper triangular, positive
     diagonal (the thin QR factor with that sign convention)."""
@@ -125,6 +125,9 @@ def test_orthonormalize_refuses_ill_conditioned_and_leaves_input(tk, ctx):
     Z = np.zeros((100, 5))
     Q, refused = _orth(tk, ctx, Z)
     assert refused == 1
+    W = rng.standard_normal((4096, 153))                          # more columns than fit in shared memory
+    Q, refused = _orth(tk, ctx, W)
+    assert refused == 1 and np.array_equal(Q, W)
     with pytest.raises(tk.TNRCudaError):
         _orth(tk, ctx, rng.standard_normal((5, 9)))               # wide
 

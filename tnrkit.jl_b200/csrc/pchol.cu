@@ -187,8 +187,9 @@ long long psd_factor(Context* ctx, const double* G, long long n, double* L, int 
 // atrg3d.jl:35,43 on an implicit operator, and svd_topk / eigh_topk in tensor_ops.cu) run
 // BETWEEN their Rayleigh-Ritz steps: those steps decide the result and keep the Householder QR +
 // Jacobi path, the steps in between only have to keep the basis well conditioned.  Refuses
-// (A untouched) when the Cholesky factor shows cond(A) >~ 1e5 or is not positive definite; the
-// caller then takes the Householder path.
+// (A untouched) when the Cholesky factor shows cond(A) >~ 1e5 or is not positive definite, or when
+// A has more than 152 columns (the small matrix must fit in shared memory); the caller then
+// takes the Householder path.
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -278,7 +279,9 @@ void chol_inv(Context* ctx, double* G, long long n, double* X, double min_ratio,
 // the factor is not safely positive definite (rank deficient or cond(A) >~ 1e5).
 bool cholqr2(Context* ctx, double* A, long long m, long long n) {
     TNR_CHECK(m >= n && n >= 1, "cholqr2: expects a tall matrix");
-    if (n > 1024 || m > 2147483647LL) return false;
+    // beyond CI_SMEM_N columns the one-CTA factorization would run on global memory (measured:
+    // TRG chi=128, 256 columns, 0.48 -> 0.86 s per step): those bases keep the Householder path
+    if (n > CI_SMEM_N || m > 2147483647LL) return false;
     double* G = dalloc(ctx, (size_t)2 * n * n);
     double* X = G + n * n;
     double* tmp = dalloc(ctx, (size_t)m * n);

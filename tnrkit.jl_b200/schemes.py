@@ -213,7 +213,9 @@ class ATRG_3D(_Sym3D, TNRScheme):
 
     `factored=True` keeps the tensor in the two-factor form `G * H` in which `_step!` produces it
     and never builds a chi^6 object (tnrkit.jl_b200/atrg3d_factored.py): truncated SVDs by
-    subspace iteration on the implicit operator, R factors by TSQR over chunks of an open bond.
+    subspace iteration on the implicit operator, R factors by TSQR over chunks of an open bond
+    (`rfactor="tsqr"`, default below chi = 40) or by pivoted Cholesky of the Gram matrices of the
+    matricizations (`rfactor="gram"`, default from chi = 40).
     `factored=None` switches to it by itself when the dense step's chi^6 tensors would not fit in
     HBM (chi >= 40).  With `shard=True` under torch.distributed (one process per GPU) the chunks
     of the open bond are divided between the ranks (all-gather of the chunk R factors and of
@@ -224,7 +226,7 @@ class ATRG_3D(_Sym3D, TNRScheme):
     DENSE_BYTES_LIMIT = 150e9
 
     def __init__(self, T, ctx=None, symmetric=None, factored=None, shard=None, group=None,
-                 max_chunk_elems=1 << 30, tol=1e-13, block=None, rfactor="tsqr", sym_chunk=None):
+                 max_chunk_elems=1 << 30, tol=1e-13, block=None, rfactor=None, sym_chunk=None):
         self._F = None
         self.block = block
         self.rfactor = rfactor
@@ -300,9 +302,14 @@ class ATRG_3D(_Sym3D, TNRScheme):
         from .atrg3d_factored import atrg3d_step_factored
 
         self._to_factored()
+        # R factors: chunked Householder TSQR (the reference's left_orth, literally) while it is
+        # affordable; from the chi where the dense step no longer fits (chi >= 40) its 4 x 2 chi^8
+        # flop and chi^2-column panels over chi^4-row chunks cost minutes per step (chi = 48:
+        # > 100 s per `_step!`), and the factors come from the Gram matrices instead (O(chi^7))
+        rf = self.rfactor or ("gram" if self.wants_factored(chi) else "tsqr")
         self._F = atrg3d_step_factored(self._F, chi, max_chunk_elems=self.max_chunk_elems,
                                        shard=self.shard, group=self.group, tol=self.tol,
-                                       block=self.block, rfactor=self.rfactor)
+                                       block=self.block, rfactor=rf)
         return self
 
     def finalize(self):
