@@ -477,8 +477,8 @@ def run_gpu(args):
         fl = step_flops(chi) if (saturated() and not atrg) else None
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         if atrg and achieved is None:
-            # no single GEMM of the factored step reaches the 1e11-flop timing threshold: the
-            # step is LAUNCH bound (see gpu_launches); report the step-level GEMM flop rate
+            # no single GEMM of the factored step reaches the 1e11-flop timing threshold: report
+            # the GEMM flop of the step over the whole step time (see gpu_launches for the rest)
             achieved = ctr["gemm_flops"] / K / sec / 1e12
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         clock_peak = 148 * DMMA_FMA_PER_CLK_SM * 2 * sm_mhz * 1e6 / 1e12
