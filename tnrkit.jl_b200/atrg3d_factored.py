@@ -210,16 +210,29 @@ def _orthonormalize(M: DeviceTensor) -> bool:
     return refused.value == 0
 
 
-def _next_check(history, it: int, rel: float, tol: float, max_jump: int = 8) -> int:
+# (rows, cols, block, kept) of an operator -> (iterations, geometric rate) of the last certified
+# subspace iteration on an operator of that shape: successive RG steps of a run converge alike, so
+# the first Rayleigh-Ritz check of the next one is placed just before the expected end instead of
+# at iterations 2 and 4 (a wrong hint only moves a check; acceptance is by the residual alone)
+_CHECK_HINT = {}
+
+
+def _next_check(history, it: int, rel: float, tol: float, max_jump: int = 8,
+                rate_hint: float | None = None) -> int:
     """Iteration of the next Rayleigh-Ritz check: where the geometric rate seen between the last
-    two checks reaches tol / 2, at most `max_jump` iterations ahead; two iterations ahead
-    while no rate is known or the residual did not shrink."""
+    two checks (or `rate_hint`, before two checks exist) reaches tol / 2, at most `max_jump`
+    iterations ahead; two iterations ahead while no rate is known or the residual did not
+    shrink."""
+    rate = None
     if history:
         it0, rel0 = history[-1]
         if 0.0 < rel < rel0 and it > it0:
             rate = (rel / rel0) ** (1.0 / (it - it0))
-            need = math.log(0.5 * tol / rel) / math.log(rate)
-            return it + int(min(max_jump, max(1, math.ceil(need))))
+    elif rate_hint is not None and 0.0 < rate_hint < 1.0:
+        rate = rate_hint
+    if rate is not None and rel > 0.0:
+        need = math.log(0.5 * tol / rel) / math.log(rate)
+        return it + int(min(max_jump, max(1, math.ceil(need))))
     return it + 2
 
 
@@ -290,7 +303,8 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     # Rayleigh-Ritz (thin SVD of A^T U, residuals) only at the iterations `check`; in between
     # the bases are just re-orthonormalised (CholeskyQR2 on the tensor cores).  The first checks
     # give the convergence rate, later ones are placed where the tolerance is predicted.
-    check, history, checks, cheap_its = min(2, maxit), [], 0, 0
+    hint = _CHECK_HINT.get((m, n, b, k)) if cholqr else None
+    check, history, checks, cheap_its = min(max(2, hint[0] - 1) if hint else 2, maxit), [], 0, 0
     it = 0
     while True:
         it += 1
@@ -350,9 +364,12 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
                 return dense_svd("subspace iteration did not certify")
             raise _lib.TNRCudaError(f"svd_topk_factored: no convergence (residual {best:.2e} "
                                     f"after {it} iterations, block {b})")
-        check = min(maxit, _next_check(history, it, rel, tol))
+        check = min(maxit, _next_check(history, it, rel, tol, rate_hint=hint[1] if hint else None))
         history.append((it, rel))
     st.update(checks=checks, cheap_iterations=cheap_its)
+    if it >= 4 and rel > 0.0:
+        # overall geometric rate of this run, from the size of a random start (~1) to `rel`
+        _CHECK_HINT[(m, n, b, k)] = (it, min(0.95, max(1e-3, rel ** (1.0 / it))))
     st.update(iterations=it, dense=False, block=b, residual=rel, rank=ke)
     if ke == k:
         Uk = DeviceTensor(Ul.buf[: m * k].clone(), rd + (k,), None, ctx)
