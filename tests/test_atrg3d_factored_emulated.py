@@ -200,6 +200,13 @@ def test_factored_atrg3d_gram_matches_tsqr_vector_chi16(tk, emu):
     s = tk.ATRG_3D(tk.classical_ising_3D(tk.Trivial), factored=True, rfactor="gram")
     got = np.array(tk.run(s, tk.truncrank(16), tk.maxiter(3), verbosity=0))
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-11
+    # and against the ORACLE's own chi = 16 run (tests/golden/baseline_sizes.json, generated by
+    # oracle/tnr_oracle.py in 380 s of host time; conditioning-checked)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_sizes.json")))
+    g = g["ATRG_3D_ising_trivial_chi16_it4"]
+    assert g["valid"]
+    oracle = np.array(g["norms"][:4])
+    assert np.max(np.abs(got - oracle) / np.abs(oracle)) <= RTOL
 
 
 def test_factored_atrg3d_chunking_is_exact(tk, emu):

@@ -79,6 +79,13 @@ def test_full_size_parity_dense_and_factored_device_steps(tk, ctx, chi):
 
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "factored_cpu_norms.json")))
     ref = np.array(g[f"ATRG_3D_ising_trivial_chi{chi}_it3"])
+    if chi == 16:
+        # chi = 16 is also within reach of the dense numpy ORACLE (380 s of host time): its norm
+        # list (tests/golden/baseline_sizes.json, conditioning-checked) is the reference there
+        o16 = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_sizes.json")))
+        o16 = o16["ATRG_3D_ising_trivial_chi16_it4"]
+        assert o16["valid"] and np.max(np.abs(np.array(o16["norms"][:4]) - ref) / np.abs(ref)) <= 1e-12
+        ref = np.array(o16["norms"][:4])
     T = tk.classical_ising_3D(tk.Trivial)
     dense = np.array(tk.run(tk.ATRG_3D(T, factored=False), tk.truncrank(chi), tk.maxiter(3),
                             verbosity=0))
