@@ -83,6 +83,11 @@ CASES = {
     "HOTRG_3D_ising_trivial_chi12_it6": (dense(o.HOTRG_3D, tk.classical_ising_3D(tk.Trivial)), 12, 6),
     "ATRG_3D_ising_trivial_chi16_it4": (dense(o.ATRG_3D, tk.classical_ising_3D(tk.Trivial)), 16, 4),
     "ATRG_3D_ising_trivial_chi10_it5": (dense(o.ATRG_3D, tk.classical_ising_3D(tk.Trivial)), 10, 5),
+    # chi = 24 (1.5 GB tensors, 13824 x 13824 SVDs: ~1 h of host time per run, ~20 GB): bonds
+    # 2 -> 4 -> 16 -> 24, so step 4 is a full-size step.  Replaces the vector that the factored step
+    # itself produced over LAPACK (factored_cpu_norms.json) as the reference of the chi = 24 tests.
+    "ATRG_3D_ising_trivial_chi24_it4": (dense(o.ATRG_3D, tk.classical_ising_3D(tk.Trivial)), 24, 4),
+    "ATRG_3D_ising_trivial_chi24_it3": (dense(o.ATRG_3D, tk.classical_ising_3D(tk.Trivial)), 24, 3),
 }
 
 if __name__ == "__main__":

@@ -264,9 +264,13 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     third factor: callers address legs by label, so no data is moved to transpose it).
 
     Block subspace iteration on the right singular subspace, block b = max(2 chi, chi + 64):
-    Z = A Q,  Z = U S W^T (thin SVD),  Y = A^T U,  Y = V' S' X^T  =>  A ~ (U X) S' V'^T;
-    accepted when max_j<chi ||A v_j - s_j u_j|| <= tol s_1 (or stalled below 20 tol, the
-    rounding floor of the products), exact (one dense SVD) when b reaches min(rows, cols).
+    Z = A Q,  U = orth(Z),  Y = A^T U,  Q = orth(Y), with CholeskyQR2 (`tnr_orthonormalize`) as
+    `orth`; at the check iterations (placed by `_next_check`) the Rayleigh-Ritz step instead:
+    Y = V' S' X^T (thin SVD)  =>  A ~ (U X) S' V'^T, accepted when
+    max_j<chi ||A v_j - s_j u_j|| <= tol s_1 (or stalled below 20 tol, the rounding floor of the
+    products).  Where CholeskyQR2 refuses (rank-deficient or ill-conditioned block: the first RG
+    steps) the thin SVD Z = U S W^T takes its place, as in round 1 (`cholqr=False`: always).
+    Exact (one dense SVD) when b reaches min(rows, cols).
     An iteration that does not certify falls back to the dense SVD of the materialised matrix
     when that has at most `dense_fallback_elems` entries, and raises otherwise: the result
     never depends on an uncertified subspace."""
@@ -303,7 +307,8 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     # Rayleigh-Ritz (thin SVD of A^T U, residuals) only at the iterations `check`; in between
     # the bases are just re-orthonormalised (CholeskyQR2 on the tensor cores).  The first checks
     # give the convergence rate, later ones are placed where the tolerance is predicted.
-    hint = _CHECK_HINT.get((m, n, b, k)) if cholqr else None
+    hint_key = (m, n, b, k, tol)
+    hint = _CHECK_HINT.get(hint_key) if cholqr else None
     check, history, checks, cheap_its = min(max(2, hint[0] - 1) if hint else 2, maxit), [], 0, 0
     it = 0
     while True:
@@ -369,7 +374,7 @@ def svd_topk_factored(F: TwoFactor, rows: str, cols: str, chi: int, tol: float =
     st.update(checks=checks, cheap_iterations=cheap_its)
     if it >= 4 and rel > 0.0:
         # overall geometric rate of this run, from the size of a random start (~1) to `rel`
-        _CHECK_HINT[(m, n, b, k)] = (it, min(0.95, max(1e-3, rel ** (1.0 / it))))
+        _CHECK_HINT[hint_key] = (it, min(0.95, max(1e-3, rel ** (1.0 / it))))
     st.update(iterations=it, dense=False, block=b, residual=rel, rank=ke)
     if ke == k:
         Uk = DeviceTensor(Ul.buf[: m * k].clone(), rd + (k,), None, ctx)
