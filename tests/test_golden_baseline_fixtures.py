@@ -55,3 +55,25 @@ def test_first_norms_of_the_fixtures_are_the_live_oracle(tk):
     T = tk.classical_ising()
     live = o.run(so.TRG_sym(np.asarray(T), T.charges, T.signs, 2), 128, 2)
     assert np.allclose(gold["TRG_ising_z2_chi128_it4"]["norms"][:3], live, rtol=1e-12)
+
+
+def test_factored_cpu_vectors_agree_with_the_oracle_where_it_has_run():
+    """tests/golden/factored_cpu_norms.json (ATRG_3D chi = 16 / 24, the factored step over LAPACK:
+    the product's own host sequencing, VERDICT r01 "half self-referential") against the dense numpy
+    ORACLE's runs at the same sizes, for every size at which the oracle fixture exists (chi = 16:
+    committed; chi = 24: ~1 h of host time per run, generated in the background of round 2).
+    With this, `device == factored CPU vector` (1e-10, tests/test_gpu_atrg3d_factored.py) is a
+    statement about the oracle."""
+    gold = _gold()
+    with open(os.path.join(HERE, "golden", "factored_cpu_norms.json")) as f:
+        fact = json.load(f)
+    checked = 0
+    for chi in (16, 24):
+        ref = np.array(fact[f"ATRG_3D_ising_trivial_chi{chi}_it3"])
+        for name in (f"ATRG_3D_ising_trivial_chi{chi}_it4", f"ATRG_3D_ising_trivial_chi{chi}_it3"):
+            if name in gold:
+                assert gold[name]["valid"], name
+                oracle = np.array(gold[name]["norms"][: len(ref)])
+                assert np.max(np.abs(oracle - ref) / np.abs(oracle)) <= 1e-11, (name, oracle, ref)
+                checked += 1
+    assert checked >= 1      # chi = 16 is committed
