@@ -96,8 +96,7 @@ def test_block_sparse_chi128_configs2(tk, ctx, name, scheme, model):
 
 @pytest.mark.parametrize("name,scheme", [
     ("HOTRG_3D_ising_trivial_chi10_it6", "HOTRG_3D"), ("HOTRG_3D_ising_trivial_chi12_it6", "HOTRG_3D"),
-    ("ATRG_3D_ising_trivial_chi10_it5", "ATRG_3D"), ("ATRG_3D_ising_trivial_chi16_it4", "ATRG_3D"),
-    ("ATRG_3D_ising_trivial_chi24_it3", "ATRG_3D"), ("ATRG_3D_ising_trivial_chi24_it4", "ATRG_3D")])
+    ("ATRG_3D_ising_trivial_chi10_it5", "ATRG_3D"), ("ATRG_3D_ising_trivial_chi16_it4", "ATRG_3D")])
 def test_3d_schemes_largest_oracle_sizes(tk, name, scheme):
     g = _case(name)
     kw = {"shard": False} if scheme == "HOTRG_3D" else {}
